@@ -1,0 +1,131 @@
+// Shared declarations for the DistilCodec B200 hot-path library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/distilcodec_b200.h"
+
+namespace dc {
+
+// ---------------------------------------------------------------- error handling (never throws across the ABI)
+void set_error(const char* fmt, ...);
+#define DC_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      dc::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));     \
+      return DC_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+#define DC_CHECK(cond, code, ...)                                                              \
+  do {                                                                                         \
+    if (!(cond)) {                                                                             \
+      dc::set_error(__VA_ARGS__);                                                              \
+      return (code);                                                                           \
+    }                                                                                          \
+  } while (0)
+#define DC_TRY(expr)                                                                           \
+  do {                                                                                         \
+    int _r = (expr);                                                                           \
+    if (_r != DC_OK) return _r;                                                                \
+  } while (0)
+
+enum { DT_F32 = 0, DT_BF16 = 1 };
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
+
+// ---------------------------------------------------------------- the one GEMM shape every dense layer maps to
+// out[b, t, n] = epi( sum_{j<J} sum_{c<C} A[b, t + shift0 + j*dil, c] * W[n, j*C + c] )
+// A is channels-last (B, T, C); rows outside [0, T) read as zero (= the conv's zero padding).
+struct ConvGemmShape {
+  int B, T, C, J, shift0, dil, N;
+};
+
+// Runtime epilogue, applied per output element v = acc:
+//   v += bias[n]; v = act(v); v *= gamma[n]; v += res[row, n]; if (add1) v = (v + add1 + add2) * scale;
+//   out0[row, n] = v;  out1[row, n] = silu(v)
+// row = b*T + t, all row-major with pitch ldo.
+struct Epilogue {
+  const float* bias = nullptr;
+  const float* gamma = nullptr;
+  const void* res = nullptr;
+  const void* add1 = nullptr;
+  const void* add2 = nullptr;
+  void* out0 = nullptr;
+  void* out1 = nullptr;
+  int act = ACT_NONE;
+  int res_dt = DT_F32, add_dt = DT_BF16, out0_dt = DT_F32, out1_dt = DT_BF16;
+  int ldo = 0;
+  float scale = 1.f;
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ float ld_as_f32(const void* p, size_t i, int dt) {
+  return dt == DT_F32 ? reinterpret_cast<const float*>(p)[i]
+                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void st_from_f32(void* p, size_t i, int dt, float v) {
+  if (dt == DT_F32) reinterpret_cast<float*>(p)[i] = v;
+  else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+// scalar epilogue (used by the fp32 CUDA-core kernel and as the definition the vector paths follow)
+__device__ __forceinline__ void epilogue_store(const Epilogue& e, size_t row, int n, float v) {
+  if (e.bias) v += e.bias[n];
+  if (e.act == ACT_GELU) v = gelu_erf_f(v);
+  else if (e.act == ACT_SILU) v = silu_f(v);
+  if (e.gamma) v *= e.gamma[n];
+  size_t o = row * (size_t)e.ldo + n;
+  if (e.res) v += ld_as_f32(e.res, o, e.res_dt);
+  if (e.add1) v = (v + ld_as_f32(e.add1, o, e.add_dt) + ld_as_f32(e.add2, o, e.add_dt)) * e.scale;
+  if (e.out0) st_from_f32(e.out0, o, e.out0_dt, v);
+  if (e.out1) st_from_f32(e.out1, o, e.out1_dt, silu_f(v));
+}
+
+// ---------------------------------------------------------------- launchers implemented across the .cu files
+// fp32 CUDA-core implicit GEMM.  A fp32 (B,T,C); W fp32 [J*C][N] (N contiguous).
+int launch_gemm_f32(const float* A, const float* W, const ConvGemmShape& s, const Epilogue& e, cudaStream_t st);
+// bf16 tcgen05 implicit GEMM.  A bf16 (B,T,C); W bf16 [N][J*C] (K contiguous).
+int launch_gemm_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
+                   cudaStream_t st, int sm_count);
+size_t gemm_tc_launch_count();
+
+// pointwise / bandwidth-bound kernels (pointwise.cu)
+int launch_transpose_ncl_to_nlc(const float* in, void* out, int out_dt, int B, int C, int T, cudaStream_t st);
+int launch_transpose_nlc_to_ncl(const float* in, float* out, int B, int T, int C, cudaStream_t st);
+// dwconv k7 (zero pad 3) + LayerNorm over C, or plain LayerNorm (dw_w == nullptr). in fp32 (B,T,C).
+int launch_dwconv_ln(const float* in, const float* dw_w /*[7][C]*/, const float* dw_b, const float* ln_w,
+                     const float* ln_b, void* out, int out_dt, int B, int T, int C, cudaStream_t st);
+int launch_cast(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st);
+int launch_gather_rows(const float* table, const int64_t* idx, int64_t nrows, int D, int64_t table_rows,
+                       float* out_f32 /*nullable*/, __nv_bfloat16* out_bf16 /*nullable*/, cudaStream_t st);
+int launch_conv_post_tanh(const void* in, int in_dt, const float* w /*[13][32]*/, float bias, float* out, int B,
+                          int L, cudaStream_t st);
+// weight prepack helpers
+int launch_weight_norm_fold(const float* g, const float* v, float* w, int dim0, int inner, cudaStream_t st);
+struct PackDesc {
+  int N, J, C;            // packed GEMM weight is N x (J*C)
+  int phases;             // N = phases * n_inner
+  long long s_n, s_c, s_k;  // source strides (elements) for (n_inner, c, kernel tap)
+  int kmap[8 * 16];       // kmap[phase*J + j] = source kernel tap or -1 (zero)
+};
+int launch_pack_weight(const float* src, const PackDesc& d, float* out_kn_f32 /*nullable*/,
+                       __nv_bfloat16* out_nk_bf16 /*nullable*/, cudaStream_t st);
+int launch_row_sqnorm(const float* in, float* out, int64_t rows, int D, cudaStream_t st);
+
+// VQ (vq.cu)
+struct VqWorkspace;
+size_t vq_workspace_bytes(int64_t nrows, int codebook_size);
+int launch_vq_search(const void* x, int x_dt, const __nv_bfloat16* x_bf16, const float* x2_opt, int64_t nrows, int D,
+                     const float* codebook_f32, const __nv_bfloat16* codebook_bf16, const float* c2, float c2max,
+                     int codebook_size, int64_t* codes, void* ws, size_t ws_bytes, float window_factor,
+                     bool use_tc, cudaStream_t st, int sm_count, int* stats_host_opt);
+
+int sm_count_of_current_device();
+
+}  // namespace dc

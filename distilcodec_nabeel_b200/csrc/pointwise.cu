@@ -1,0 +1,333 @@
+// Bandwidth-bound kernels of the hot path (vectorised, coalesced, one pass over HBM each) and the one-time
+// weight prepack kernels.  All activations are channels-last (rows = frames, C contiguous).
+#include "common.cuh"
+
+namespace dc {
+
+static thread_local uint64_t g_launches_pw = 0;
+uint64_t pointwise_launch_count() { return g_launches_pw; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------ transposes
+// (B, C, T) fp32 -> (B, T, C) fp32|bf16 ; 32x32 tiles through padded shared memory, coalesced both ways.
+template <typename TOut>
+__global__ void transpose_ncl_to_nlc_kernel(const float* __restrict__ in, TOut* __restrict__ out, int C, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const float* ib = in + (size_t)b * C * T;
+  TOut* ob = out + (size_t)b * C * T;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? ib[(size_t)c * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < C) {
+      float v = tile[threadIdx.x][i];
+      if constexpr (sizeof(TOut) == 4) ob[(size_t)t * C + c] = v;
+      else ob[(size_t)t * C + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+int launch_transpose_ncl_to_nlc(const float* in, void* out, int out_dt, int B, int C, int T, cudaStream_t st) {
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  if (out_dt == DT_F32) transpose_ncl_to_nlc_kernel<float><<<grid, block, 0, st>>>(in, (float*)out, C, T);
+  else transpose_ncl_to_nlc_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(in, (__nv_bfloat16*)out, C, T);
+  ++g_launches_pw;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+int launch_transpose_nlc_to_ncl(const float* in, float* out, int B, int T, int C, cudaStream_t st) {
+  // (B,T,C) -> (B,C,T) is the same kernel with the roles of C and T swapped
+  dim3 grid((C + 31) / 32, (T + 31) / 32, B), block(32, 8);
+  transpose_ncl_to_nlc_kernel<float><<<grid, block, 0, st>>>(in, out, T, C);
+  ++g_launches_pw;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ dwconv7 + LayerNorm
+// One warp per frame.  Lane l owns channels {(i*32 + l)*4 .. +3}.  Depthwise taps come from the 7 neighbouring
+// rows (L1/L2 absorb the 7x overlap; DRAM sees each row once).  LayerNorm is two-pass in registers, biased
+// variance, eps 1e-6 (F.layer_norm / the manual channels_first form, models/convnext_utils.py:203-213).
+// Algorithmic HBM bytes per frame: C*4 read + C*sizeof(TOut) written.
+template <int VPL /*float4 groups per lane*/, bool CONV, typename TOut>
+__global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict__ in, const float* __restrict__ dw_w,
+                                                        const float* __restrict__ dw_b,
+                                                        const float* __restrict__ ln_w,
+                                                        const float* __restrict__ ln_b, TOut* __restrict__ out,
+                                                        int B, int T) {
+  constexpr int C = VPL * 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= (long long)B * T) return;
+  const int t = (int)(row % T);
+  const float* rp = in + (size_t)row * C;
+
+  float4 y[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if constexpr (CONV) {
+      float4 a = __ldg(reinterpret_cast<const float4*>(dw_b + c));
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int tt = t + j - 3;
+        if (tt >= 0 && tt < T) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(rp + (long long)(j - 3) * C + c));
+          const float4 w = __ldg(reinterpret_cast<const float4*>(dw_w + (size_t)j * C + c));
+          a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y); a.z = fmaf(x.z, w.z, a.z); a.w = fmaf(x.w, w.w, a.w);
+        }
+      }
+      y[i] = a;
+    } else {
+      y[i] = __ldg(reinterpret_cast<const float4*>(rp + c));
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) s += (y[i].x + y[i].y) + (y[i].z + y[i].w);
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float a = y[i].x - mean, b = y[i].y - mean, c = y[i].z - mean, d = y[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + 1e-6f);
+  TOut* op = out + (size_t)row * C;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(ln_w + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(ln_b + c));
+    float4 o;
+    o.x = (y[i].x - mean) * rstd * w.x + b.x;
+    o.y = (y[i].y - mean) * rstd * w.y + b.y;
+    o.z = (y[i].z - mean) * rstd * w.z + b.z;
+    o.w = (y[i].w - mean) * rstd * w.w + b.w;
+    if constexpr (sizeof(TOut) == 4) {
+      *reinterpret_cast<float4*>(op + c) = o;
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(op + c) = pk;
+    }
+  }
+}
+
+template <int VPL>
+static int dwconv_ln_dispatch(const float* in, const float* dw_w, const float* dw_b, const float* ln_w,
+                              const float* ln_b, void* out, int out_dt, int B, int T, cudaStream_t st) {
+  const long long rows = (long long)B * T;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (dw_w) {
+    if (out_dt == DT_F32) dwconv_ln_kernel<VPL, true, float><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (float*)out, B, T);
+    else dwconv_ln_kernel<VPL, true, __nv_bfloat16><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (__nv_bfloat16*)out, B, T);
+  } else {
+    if (out_dt == DT_F32) dwconv_ln_kernel<VPL, false, float><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (float*)out, B, T);
+    else dwconv_ln_kernel<VPL, false, __nv_bfloat16><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (__nv_bfloat16*)out, B, T);
+  }
+  ++g_launches_pw;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+int launch_dwconv_ln(const float* in, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b,
+                     void* out, int out_dt, int B, int T, int C, cudaStream_t st) {
+  switch (C) {
+    case 256: return dwconv_ln_dispatch<2>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
+    case 512: return dwconv_ln_dispatch<4>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
+    case 768: return dwconv_ln_dispatch<6>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
+    case 1024: return dwconv_ln_dispatch<8>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
+    default: set_error("dwconv_ln: unsupported channel count %d (256/512/768/1024)", C); return DC_ERR_SHAPE;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ cast
+__global__ void cast_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 v = __ldg(in + i);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    out[i] = pk;
+  }
+}
+int launch_cast(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st) {
+  DC_CHECK(n % 4 == 0, DC_ERR_SHAPE, "cast: element count must be a multiple of 4");
+  const size_t n4 = n / 4;
+  if (n4 == 0) return DC_OK;
+  unsigned grid = (unsigned)((n4 + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  cast_kernel<<<grid, 256, 0, st>>>((const float4*)in, (uint2*)out, n4);
+  ++g_launches_pw;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ codebook gather
+// batched_embedding / einx.get_at (vector_quantize_pytorch.py:243-247, residual_vq.py:123): out[r,:] = table[idx[r],:]
+// one warp per row, float4 loads; writes the fp32 row (API output quantized_fup) and/or a bf16 copy (GEMM operand).
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ table,
+                                                          const int64_t* __restrict__ idx, int64_t nrows, int D,
+                                                          int64_t table_rows, float* __restrict__ o32,
+                                                          __nv_bfloat16* __restrict__ o16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= nrows) return;
+  int64_t k = idx[row];
+  k = k < 0 ? 0 : (k >= table_rows ? table_rows - 1 : k);  // the reference would raise; never read out of bounds
+  const float4* src = reinterpret_cast<const float4*>(table + (size_t)k * D);
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 v = __ldg(src + i);
+    if (o32) reinterpret_cast<float4*>(o32 + (size_t)row * D)[i] = v;
+    if (o16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(o16 + (size_t)row * D)[i] = pk;
+    }
+  }
+}
+int launch_gather_rows(const float* table, const int64_t* idx, int64_t nrows, int D, int64_t table_rows, float* o32,
+                       __nv_bfloat16* o16, cudaStream_t st) {
+  if (nrows == 0) return DC_OK;
+  gather_rows_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(table, idx, nrows, D, table_rows, o32, o16);
+  ++g_launches_pw;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ conv_post + tanh
+// Conv1d(32 -> 1, k13, pad 6) + tanh (models/generators.py:141-145) on the already SiLU'd channels-last input.
+// 256 outputs per block; the (256+12) x 32 input slab is staged in padded shared memory (row pitch 33 words).
+template <typename TIn>
+__global__ void __launch_bounds__(256) conv_post_tanh_kernel(const TIn* __restrict__ in, const float* __restrict__ w,
+                                                             float bias, float* __restrict__ out, int L) {
+  constexpr int C = 32, K = 13, TILE = 256;
+  __shared__ float sx[(TILE + K - 1) * 33];
+  __shared__ float sw[K * C];
+  const int b = blockIdx.y, l0 = blockIdx.x * TILE;
+  const TIn* ib = in + (size_t)b * L * C;
+  for (int i = threadIdx.x; i < K * C; i += 256) sw[i] = w[i];
+  for (int i = threadIdx.x; i < (TILE + K - 1) * C; i += 256) {
+    const int r = i / C, c = i % C, l = l0 + r - 6;
+    float v = 0.f;
+    if (l >= 0 && l < L) {
+      if constexpr (sizeof(TIn) == 4) v = ib[(size_t)l * C + c];
+      else v = __bfloat162float(ib[(size_t)l * C + c]);
+    }
+    sx[r * 33 + c] = v;
+  }
+  __syncthreads();
+  const int l = l0 + threadIdx.x;
+  if (l >= L) return;
+  float acc = bias;
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc = fmaf(sx[(threadIdx.x + j) * 33 + c], sw[j * C + c], acc);
+  out[(size_t)b * L + l] = tanhf(acc);
+}
+int launch_conv_post_tanh(const void* in, int in_dt, const float* w, float bias, float* out, int B, int L,
+                          cudaStream_t st) {
+  dim3 grid((L + 255) / 256, B);
+  if (in_dt == DT_F32) conv_post_tanh_kernel<float><<<grid, 256, 0, st>>>((const float*)in, w, bias, out, L);
+  else conv_post_tanh_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, w, bias, out, L);
+  ++g_launches_pw;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ prepack (one-time)
+// weight_norm fold: w[i,:] = g[i] * v[i,:] / ||v[i,:]||_2   (torch._weight_norm, dim = 0)
+__global__ void weight_norm_fold_kernel(const float* __restrict__ g, const float* __restrict__ v,
+                                        float* __restrict__ w, int inner) {
+  __shared__ float red[32];
+  const int i = blockIdx.x;
+  const float* vi = v + (size_t)i * inner;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < inner; k += blockDim.x) s = fmaf(vi[k], vi[k], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float scale = g[i] / sqrtf(red[0]);
+  for (int k = threadIdx.x; k < inner; k += blockDim.x) w[(size_t)i * inner + k] = vi[k] * scale;
+}
+int launch_weight_norm_fold(const float* g, const float* v, float* w, int dim0, int inner, cudaStream_t st) {
+  weight_norm_fold_kernel<<<dim0, 256, 0, st>>>(g, v, w, inner);
+  ++g_launches_pw;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+// generic repack of a Conv1d (O,I,k) / ConvTranspose1d (I,O,k) / Linear (O,I) weight into the GEMM operand
+//   Wp[n][j*C + c],  n = phase * n_inner + ni,  source = src[ni*s_n + c*s_c + kmap[phase][j]*s_k] (0 if kmap < 0)
+__global__ void pack_weight_kernel(const float* __restrict__ src, PackDesc d, float* __restrict__ o_kn,
+                                   __nv_bfloat16* __restrict__ o_nk) {
+  const long long K = (long long)d.J * d.C, total = K * d.N;
+  const int n_inner = d.N / d.phases;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / K);
+    const int k = (int)(i % K);
+    const int j = k / d.C, c = k % d.C;
+    const int ph = n / n_inner, ni = n % n_inner;
+    const int kk = d.kmap[ph * d.J + j];
+    const float v = kk < 0 ? 0.f : src[ni * d.s_n + c * d.s_c + kk * d.s_k];
+    if (o_kn) o_kn[(size_t)k * d.N + n] = v;
+    if (o_nk) o_nk[(size_t)n * K + k] = __float2bfloat16_rn(v);
+  }
+}
+int launch_pack_weight(const float* src, const PackDesc& d, float* o_kn, __nv_bfloat16* o_nk, cudaStream_t st) {
+  DC_CHECK(d.phases * d.J <= 8 * 16, DC_ERR_SHAPE, "pack_weight: tap table too large");
+  pack_weight_kernel<<<148 * 8, 256, 0, st>>>(src, d, o_kn, o_nk);
+  ++g_launches_pw;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+// row squared norms, fp64 accumulate, correctly rounded to fp32 (||c||^2 of the codebook; default ||x||^2)
+__global__ void __launch_bounds__(256) row_sqnorm_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                         int64_t rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* p = reinterpret_cast<const float4*>(in + (size_t)row * D);
+  double s = 0.0;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 v = __ldg(p + i);
+    s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = (float)s;
+}
+int launch_row_sqnorm(const float* in, float* out, int64_t rows, int D, cudaStream_t st) {
+  if (rows == 0) return DC_OK;
+  row_sqnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(in, out, rows, D);
+  ++g_launches_pw;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+}  // namespace dc

@@ -1,0 +1,131 @@
+/* distilcodec_b200.h — C ABI of libdistilcodec_b200.so
+ *
+ * B200-native (sm_100a) implementation of the DistilCodec inference hot path
+ *   mel -> ConvNeXt encoder -> single-codebook Euclidean VQ (32768 x 3584) -> HiFiGAN-style decoder -> wav.
+ *
+ * The reference (nabeelscicom/DistilCodec_nabeel) has no FFI; its boundary is the attribute triple
+ * `self.encoder / self.quantizer / self.generator` of `DistilCodec` (distilcodec/distil_codec.py:52-54).
+ * Each entry point below replaces one call the reference's API makes on those attributes; the file:line of the
+ * replaced interface is cited on every function.  INTEGRATION.md shows the Python (ctypes) binding.
+ *
+ * Conventions
+ *   - every function returns 0 (DC_OK) or a negative dc_status; dc_last_error() gives the message (thread-local)
+ *   - all pointers named *_dev are device pointers on the handle's device; the caller (PyTorch's caching
+ *     allocator in the shipped host side) owns every input, output and workspace buffer
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it, no hidden
+ *     synchronisation or allocation after dc_finalize()
+ *   - activations cross the ABI time-major / channels-last ("NLC": (B, T, C) row-major) unless stated otherwise;
+ *     the reference's channels-first (B, C, T) tensors are strided views of the same memory
+ *   - a handle is bound to one device and one numeric mode and is not re-entrant
+ */
+#ifndef DISTILCODEC_B200_H_
+#define DISTILCODEC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dc_handle_s* dc_handle;
+
+typedef enum {
+  DC_OK = 0,
+  DC_ERR_ARG = -1,       /* null pointer, bad enum, unknown tensor name                     */
+  DC_ERR_SHAPE = -2,     /* shape not supported by the kernels                              */
+  DC_ERR_CUDA = -3,      /* a CUDA runtime / driver call failed                             */
+  DC_ERR_ARCH = -4,      /* device is not compute capability 10.x                           */
+  DC_ERR_STATE = -5,     /* call order violated (e.g. forward before finalize)              */
+  DC_ERR_WORKSPACE = -6  /* workspace too small (see dc_workspace_bytes)                    */
+} dc_status;
+
+/* numeric mode: what `enable_bfloat16` selects in the reference API (distil_codec.py:545,550,581,590) */
+typedef enum {
+  DC_MODE_FP32 = 0, /* CUDA-core fp32 kernels; parity target 1e-4                                  */
+  DC_MODE_BF16 = 1  /* tcgen05 tensor-core kernels, bf16 operands / fp32 accumulate; target 1e-2   */
+} dc_mode;
+
+typedef enum { DC_STAGE_ENCODER = 0, DC_STAGE_QUANTIZER = 1, DC_STAGE_DECODE_CODES = 2, DC_STAGE_GENERATOR = 3 } dc_stage;
+
+int dc_version(void);
+const char* dc_last_error(void);
+
+/* Lifetime.  Replaces module construction + `.to(device)` (distil_codec.py:52-54, 72-75). */
+int dc_create(int device, int mode, dc_handle* out);
+int dc_destroy(dc_handle h);
+
+/* Weight ingestion.  Replaces `load_state_dict` on the three modules (distil_codec.py:91-94): call once per
+ * state_dict entry with the reference's key (prefixed `encoder.` / `quantizer.` / `generator.`), an fp32 device
+ * pointer and the tensor's shape; then dc_finalize() folds weight_norm (models/generators.py:50,70,106),
+ * repacks every matrix into the kernels' layouts and precomputes ||c||^2.  The library copies what it needs;
+ * only `quantizer.grvq.rvqs.0.layers.0._codebook.embed` (470 MB fp32) is referenced in place and must stay
+ * alive and unmodified until the next dc_finalize() or dc_destroy(). */
+int dc_set_tensor(dc_handle h, const char* name, const float* data_dev, const int64_t* shape, int ndim);
+int dc_finalize(dc_handle h, void* stream);
+
+/* Scratch requirement of one stage for a batch of B clips x T frames. */
+int dc_workspace_bytes(dc_handle h, int stage, int B, int T, size_t* bytes);
+
+/* encoder(mel): ConvNeXtEncoder.forward, models/encoders.py:68-76 (call sites distil_codec.py:520,551).
+ *   mel_ncl_dev : fp32 (B, 128, T) channels-first, exactly what LogMelSpectrogram emits
+ *   enc_nlc_dev : fp32 (B, T, 1024) */
+int dc_encoder_forward(dc_handle h, const float* mel_ncl_dev, int B, int T, float* enc_nlc_dev, void* ws_dev,
+                       size_t ws_bytes, void* stream);
+
+/* quantizer(enc): DownsampleGRVQ.forward, vector_quantization/grfvq.py:105-132 (call sites distil_codec.py:525,555).
+ *   enc_nlc_dev       : fp32 (B, T, 1024)
+ *   codes_dev         : int64 (B, T)            == GRVQResult.codes[0, :, :, 0]
+ *   x_pjt_in_dev      : (B, T, 3584) bf16 in DC_MODE_BF16, fp32 in DC_MODE_FP32   == GRVQResult.x_pjt_in
+ *   fup_dev           : fp32 (B, T, 3584)       == GRVQResult.quantized_fup (codebook rows); nullable
+ *   quantized_nlc_dev : fp32 (B, T, 1024)       == GRVQResult.quantized viewed channels-last */
+int dc_quantizer_forward(dc_handle h, const float* enc_nlc_dev, int B, int T, int64_t* codes_dev, void* x_pjt_in_dev,
+                         float* fup_dev, float* quantized_nlc_dev, void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Nearest-code search only: EuclideanCodebook.forward eval path, vector_quantization/utils/
+ * vector_quantize_pytorch.py:462-538 (cdist :41-45, argmax :96).  Returns exactly
+ *   argmax_j -sqrt(max((x2 + c2_j) + (-2 * x.c_j), 0))   with the lowest index on ties,
+ * all in fp32 like the reference, with x.c_j evaluated exactly (fp64) then rounded to fp32.
+ *   x_dev    : (N, 3584) rows, dtype x_is_bf16 ? bf16 : fp32
+ *   x2_dev   : optional fp32 (N) row square-norms as the caller's reference computes them (strict parity with
+ *              a particular reduction order); NULL = correctly rounded exact sum
+ *   stats_host : optional int[4] {rows, rescored candidates, rows sent to the exhaustive pass, 0}; forces a sync */
+int dc_vq_search(dc_handle h, const void* x_dev, int x_is_bf16, const float* x2_dev, int64_t N, int64_t* codes_dev,
+                 void* ws_dev, size_t ws_bytes, void* stream, int* stats_host);
+int dc_vq_workspace_bytes(dc_handle h, int64_t N, size_t* bytes);
+
+/* quantizer.decode(indices): DownsampleGRVQ.decode, grfvq.py:141-146 -> get_output_from_indices,
+ * utils/residual_vq.py:301-303,135-138 (call sites distil_codec.py:591,630).
+ *   codes_dev : int64 (B, T);  z_nlc_dev : fp32 (B, T, 1024) */
+int dc_quantizer_decode(dc_handle h, const int64_t* codes_dev, int B, int T, float* z_nlc_dev, void* ws_dev,
+                        size_t ws_bytes, void* stream);
+
+/* generator(z): HiFiGANGenerator.forward, models/generators.py:118-147 (call sites distil_codec.py:528,577,592,631).
+ *   z_nlc_dev : fp32 (B, T, 1024);  wav_dev : fp32 (B, 256*T) */
+int dc_generator_forward(dc_handle h, const float* z_nlc_dev, int B, int T, float* wav_dev, void* ws_dev,
+                         size_t ws_bytes, void* stream);
+
+/* Layout helpers between the reference's channels-first tensors and the ABI's channels-last ones. */
+int dc_ncl_to_nlc(const float* in_dev, float* out_dev, int B, int C, int T, void* stream);
+int dc_nlc_to_ncl(const float* in_dev, float* out_dev, int B, int T, int C, void* stream);
+
+/* ---- op-level entry points (used by the parity tests and micro-benchmarks; same kernels as the stages) ---- */
+
+/* Shifted-row implicit-GEMM convolution, the one shape every dense layer of the path maps to:
+ *   out[b,t,n] = act( sum_{j<J} sum_{c<C} a[b, t + shift0 + j*dil, c] * w[n, j*C + c] + bias[n] ) (+ res[b,t,n])
+ * a (B,T,C), w (N, J*C), bias (N) or NULL, res/out (B,T,N); all fp32 device arrays (bf16 mode rounds a and w to
+ * bf16 and runs the tcgen05 kernel, fp32 mode runs the CUDA-core kernel).  act: 0 none, 1 exact GELU, 2 SiLU. */
+int dc_op_conv_gemm(dc_handle h, const float* a_dev, const float* w_dev, const float* bias_dev, const float* res_dev,
+                    float* out_dev, int B, int T, int C, int J, int shift0, int dil, int N, int act, void* stream);
+/* depthwise k7 conv + LayerNorm(eps 1e-6) over C of a channels-last fp32 tensor (models/convnext_utils.py:265-268);
+ * dw_w_dev (C,1,7) reference layout or NULL for LayerNorm only (convnext_utils.py:203-213). */
+int dc_op_dwconv_ln(dc_handle h, const float* in_dev, const float* dw_w_dev, const float* dw_b_dev,
+                    const float* ln_w_dev, const float* ln_b_dev, float* out_dev, int B, int T, int C, void* stream);
+
+/* number of kernels this library has launched on the calling thread since load (bench.py's gpu_launches) */
+uint64_t dc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISTILCODEC_B200_H_ */
