@@ -1,0 +1,1007 @@
+// C ABI of libdistilcodec_b200.so (include/distilcodec_b200.h): handle, weight ingestion + prepack, and the four
+// stage entry points that replace the reference's module calls
+//   encoder(mel)            models/encoders.py:68-76
+//   quantizer(enc)          vector_quantization/grfvq.py:105-132
+//   quantizer.decode(codes) vector_quantization/grfvq.py:141-146
+//   generator(z)            models/generators.py:118-147
+// Every dense layer is one shifted-row implicit GEMM (gemm_tc.cu in DC_MODE_BF16, gemm_f32.cu in DC_MODE_FP32) with
+// the bias / activation / LayerScale / residual / 3-branch mean fused in its epilogue; depthwise conv + LayerNorm
+// and the remaining element-wise work are the bandwidth kernels of pointwise.cu; the codebook search is vq.cu.
+// Activations are channels-last (rows = frames).  No allocation and no synchronisation after dc_finalize().
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace dc {
+
+// ---------------------------------------------------------------------------------------------- errors
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+size_t gemm_tc_launch_count();
+
+int sm_count_of_current_device() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------- small kernels
+static thread_local uint64_t g_launches_api = 0;
+
+__global__ void max_reduce_kernel(const float* __restrict__ in, int n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, in[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+    *out = m;
+  }
+}
+__global__ void tile_bias_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int reps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * reps) out[i] = in[i % n];
+}
+
+// ---------------------------------------------------------------------------------------------- handle
+struct RawTensor {
+  float* d = nullptr;
+  std::vector<int64_t> shape;
+  size_t numel = 0;
+  bool owned = false;
+};
+
+struct Dense {  // one shifted-row implicit GEMM layer
+  int C = 0, J = 1, shift0 = 0, dil = 1, N = 0;
+  __nv_bfloat16* w_bf16 = nullptr;  // [N][J*C]   (DC_MODE_BF16)
+  float* w_f32 = nullptr;           // [J*C][N]   (DC_MODE_FP32)
+  const float* bias = nullptr;      // [N]
+};
+
+struct Block {  // ConvNeXtBlock, models/convnext_utils.py:217-282
+  int C = 0;
+  const float *dw_w = nullptr /*[7][C]*/, *dw_b = nullptr, *ln_w = nullptr, *ln_b = nullptr, *gamma = nullptr;
+  Dense pw1, pw2;
+};
+
+struct Arena {  // bump allocator over the caller's workspace; base == nullptr counts only
+  char* base = nullptr;
+  size_t off = 0, cap = 0, peak = 0;
+  void* get(size_t bytes) {
+    const size_t a = (off + 1023) / 1024 * 1024;
+    off = a + bytes;
+    if (off > peak) peak = off;
+    return base ? base + a : reinterpret_cast<void*>(uintptr_t(1024));
+  }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+}  // namespace dc
+
+using namespace dc;
+
+struct dc_handle_s {
+  int device = 0, mode = DC_MODE_BF16, sm_count = 148;
+  dc_config cfg;
+  bool finalized = false;
+  std::map<std::string, RawTensor> raw;
+  std::vector<void*> owned;
+  float vq_window = 0.25f;
+  bool vq_tc = true;
+  bool vq_x2_exact = false;
+
+  // encoder
+  Dense stem;
+  const float *stem_ln_w = nullptr, *stem_ln_b = nullptr;
+  const float *down_ln_w[4] = {}, *down_ln_b[4] = {};
+  Dense down_conv[4];
+  std::vector<Block> enc_blocks[4];
+  const float *final_ln_w = nullptr, *final_ln_b = nullptr;
+  // quantizer
+  Dense q_down, proj_in, proj_out, q_up;
+  Block q_down_blk, q_up_blk;
+  const float* codebook = nullptr;  // (K, CD) fp32, referenced in place
+  __nv_bfloat16* codebook_bf16 = nullptr;
+  float *c2 = nullptr, *c2max = nullptr;
+  int K = 0, CD = 0;
+  // generator
+  Dense conv_pre, ups[8], rb[8][3][2][3];
+  float* post_w = nullptr;  // [k][C_last]
+  float post_b = 0.f;
+  int post_C = 0;
+};
+
+namespace dc {
+
+static int act_dt(const dc_handle_s* h) { return h->mode == DC_MODE_BF16 ? DT_BF16 : DT_F32; }
+static size_t act_es(const dc_handle_s* h) { return h->mode == DC_MODE_BF16 ? 2 : 4; }
+
+template <typename T>
+static int dev_alloc(dc_handle_s* h, T** out, size_t count) {
+  void* p = nullptr;
+  DC_CUDA(cudaMalloc(&p, count * sizeof(T) > 0 ? count * sizeof(T) : 16));
+  h->owned.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return DC_OK;
+}
+
+static const RawTensor* find_raw(const dc_handle_s* h, const std::string& name) {
+  auto it = h->raw.find(name);
+  return it == h->raw.end() ? nullptr : &it->second;
+}
+#define DC_GET_RAW(var, name)                                                                  \
+  const RawTensor* var = find_raw(h, (name));                                                  \
+  DC_CHECK(var != nullptr, DC_ERR_STATE, "missing tensor '%s' (call dc_set_tensor for every state_dict entry)", \
+           std::string(name).c_str())
+
+// ---- weight packing -------------------------------------------------------------------------------------
+// src: fp32 device weight; Conv1d (O, I, k) / Linear (O, I): transposed=false; ConvTranspose1d (I, O, k): true.
+static int pack_dense(dc_handle_s* h, const float* src, bool transposed, int O, int I, int k, int stride, int pad,
+                      int dil, const float* bias, Dense* d, cudaStream_t st) {
+  PackDesc pd;
+  memset(&pd, 0, sizeof(pd));
+  pd.C = I;
+  if (!transposed) {
+    d->J = k;
+    d->shift0 = -pad;
+    d->dil = dil;
+    d->N = O;
+    pd.phases = 1;
+    pd.s_n = (long long)I * k;
+    pd.s_c = k;
+    pd.s_k = 1;
+    DC_CHECK(k <= 128, DC_ERR_SHAPE, "conv kernel size %d too large", k);
+    for (int j = 0; j < k; ++j) pd.kmap[j] = j;
+  } else {
+    // out[o, q*stride + ph] = sum_i sum_kk x[i, t] w[i, o, kk],  q*stride + ph = t*stride - pad + kk
+    //  => kk = ph + pad - sh*stride for input shift sh = t - q
+    int sh_min = 1 << 30, sh_max = -(1 << 30);
+    for (int ph = 0; ph < stride; ++ph)
+      for (int kk = 0; kk < k; ++kk)
+        if ((ph + pad - kk) % stride == 0) {
+          const int sh = (ph + pad - kk) / stride;
+          sh_min = sh < sh_min ? sh : sh_min;
+          sh_max = sh > sh_max ? sh : sh_max;
+        }
+    d->J = sh_max - sh_min + 1;
+    d->shift0 = sh_min;
+    d->dil = 1;
+    d->N = stride * O;
+    pd.phases = stride;
+    pd.s_n = k;
+    pd.s_c = (long long)O * k;
+    pd.s_k = 1;
+    DC_CHECK(stride * d->J <= 128, DC_ERR_SHAPE, "conv-transpose tap table too large");
+    for (int ph = 0; ph < stride; ++ph)
+      for (int j = 0; j < d->J; ++j) {
+        const int kk = ph + pad - (sh_min + j) * stride;
+        pd.kmap[ph * d->J + j] = (kk >= 0 && kk < k) ? kk : -1;
+      }
+  }
+  d->C = I;
+  pd.N = d->N;
+  pd.J = d->J;
+  const size_t elems = (size_t)d->N * d->J * d->C;
+  if (h->mode == DC_MODE_BF16) {
+    DC_TRY(dev_alloc(h, &d->w_bf16, elems));
+    DC_TRY(launch_pack_weight(src, pd, nullptr, d->w_bf16, st));
+  } else {
+    DC_TRY(dev_alloc(h, &d->w_f32, elems));
+    DC_TRY(launch_pack_weight(src, pd, d->w_f32, nullptr, st));
+  }
+  if (bias && transposed && stride > 1) {
+    float* b = nullptr;
+    DC_TRY(dev_alloc(h, &b, (size_t)d->N));
+    tile_bias_kernel<<<(d->N + 255) / 256, 256, 0, st>>>(bias, b, O, stride);
+    ++g_launches_api;
+    DC_CUDA(cudaGetLastError());
+    d->bias = b;
+  } else {
+    d->bias = bias;
+  }
+  return DC_OK;
+}
+
+static int pack_conv1d(dc_handle_s* h, const std::string& p, int dil, Dense* d, cudaStream_t st) {
+  DC_GET_RAW(w, p + "weight");
+  DC_GET_RAW(b, p + "bias");
+  DC_CHECK(w->shape.size() == 3 || w->shape.size() == 2, DC_ERR_SHAPE, "%sweight: expected 2-D or 3-D", p.c_str());
+  const int O = (int)w->shape[0], I = (int)w->shape[1], k = w->shape.size() == 3 ? (int)w->shape[2] : 1;
+  return pack_dense(h, w->d, false, O, I, k, 1, dil * (k - 1) / 2, dil, b->d, d, st);
+}
+
+// weight_norm-parametrised conv (generator): w = g * v / ||v|| over all dims but 0 (torch._weight_norm, dim 0)
+static int pack_wn_conv(dc_handle_s* h, const std::string& p, bool transposed, int stride, int pad, int dil, Dense* d,
+                        float* scratch, cudaStream_t st) {
+  DC_GET_RAW(g, p + "parametrizations.weight.original0");
+  DC_GET_RAW(v, p + "parametrizations.weight.original1");
+  DC_GET_RAW(b, p + "bias");
+  DC_CHECK(v->shape.size() == 3, DC_ERR_SHAPE, "%s: weight_norm v must be 3-D", p.c_str());
+  const int d0 = (int)v->shape[0], d1 = (int)v->shape[1], k = (int)v->shape[2];
+  DC_TRY(launch_weight_norm_fold(g->d, v->d, scratch, d0, d1 * k, st));
+  if (transposed) return pack_dense(h, scratch, true, d1, d0, k, stride, pad, 1, b->d, d, st);
+  return pack_dense(h, scratch, false, d0, d1, k, 1, pad, dil, b->d, d, st);
+}
+
+static int pack_block(dc_handle_s* h, const std::string& p, Block* blk, cudaStream_t st) {
+  DC_GET_RAW(gamma, p + "gamma");
+  DC_GET_RAW(dw, p + "dwconv.weight");
+  DC_GET_RAW(dwb, p + "dwconv.bias");
+  DC_GET_RAW(lw, p + "norm.weight");
+  DC_GET_RAW(lb, p + "norm.bias");
+  const int C = (int)gamma->numel;
+  DC_CHECK(dw->shape.size() == 3 && dw->shape[0] == C && dw->shape[2] == 7, DC_ERR_SHAPE,
+           "%sdwconv.weight must be (C,1,7)", p.c_str());
+  blk->C = C;
+  blk->gamma = gamma->d;
+  blk->dw_b = dwb->d;
+  blk->ln_w = lw->d;
+  blk->ln_b = lb->d;
+  float* dwt = nullptr;
+  DC_TRY(dev_alloc(h, &dwt, (size_t)7 * C));
+  PackDesc pd;
+  memset(&pd, 0, sizeof(pd));
+  pd.N = 1; pd.J = 7; pd.C = C; pd.phases = 1; pd.s_n = 0; pd.s_c = 7; pd.s_k = 1;
+  for (int j = 0; j < 7; ++j) pd.kmap[j] = j;
+  DC_TRY(launch_pack_weight(dw->d, pd, dwt, nullptr, st));  // [7][C]
+  blk->dw_w = dwt;
+  DC_TRY(pack_conv1d(h, p + "pwconv1.", 1, &blk->pw1, st));
+  DC_TRY(pack_conv1d(h, p + "pwconv2.", 1, &blk->pw2, st));
+  return DC_OK;
+}
+
+// ---- layer runners --------------------------------------------------------------------------------------
+static int run_dense(const dc_handle_s* h, const Dense& d, const void* A, int B, int T, Epilogue ep, cudaStream_t st) {
+  ConvGemmShape s{B, T, d.C, d.J, d.shift0, d.dil, d.N};
+  if (!ep.bias) ep.bias = d.bias;
+  ep.ldo = d.N;
+  if (h->mode == DC_MODE_BF16)
+    return launch_gemm_tc(reinterpret_cast<const __nv_bfloat16*>(A), d.w_bf16, s, ep, st, h->sm_count);
+  return launch_gemm_f32(reinterpret_cast<const float*>(A), d.w_f32, s, ep, st);
+}
+
+// x (fp32, B*T x C) <- x + gamma * pw2(gelu(pw1(LN(dwconv(x)))))     (convnext_utils.py:263-282)
+// a: B*T x C operand scratch, hid: B*T x 4C operand scratch; out (default x) receives the result,
+// out1_copy (optional) an operand-dtype copy of it.
+static int run_block(const dc_handle_s* h, const Block& blk, float* x, void* a, void* hid, int B, int T, float* out,
+                     void* out1_copy, bool dry, cudaStream_t st) {
+  if (dry) return DC_OK;
+  const int ad = act_dt(h);
+  DC_TRY(launch_dwconv_ln(x, blk.dw_w, blk.dw_b, blk.ln_w, blk.ln_b, a, ad, B, T, blk.C, st));
+  Epilogue e1;
+  e1.act = ACT_GELU;
+  e1.out0 = hid;
+  e1.out0_dt = ad;
+  DC_TRY(run_dense(h, blk.pw1, a, B, T, e1, st));
+  Epilogue e2;
+  e2.gamma = blk.gamma;
+  e2.res = x;
+  e2.res_dt = DT_F32;
+  e2.out0 = out ? out : x;
+  e2.out0_dt = DT_F32;
+  if (out1_copy) {
+    e2.out1 = out1_copy;
+    e2.out1_dt = ad;
+    e2.out1_silu = 0;
+  }
+  DC_TRY(run_dense(h, blk.pw2, hid, B, T, e2, st));
+  return DC_OK;
+}
+
+// ---- stages ---------------------------------------------------------------------------------------------
+static int stage_encoder(const dc_handle_s* h, const float* mel_ncl, int B, int T, float* enc_out, Arena& ar, bool dry,
+                         cudaStream_t st) {
+  const size_t rows = (size_t)B * T, es = act_es(h);
+  const int ad = act_dt(h);
+  const dc_config& c = h->cfg;
+  int maxdim = 0;
+  for (int s = 0; s < 4; ++s) maxdim = c.enc_dims[s] > maxdim ? c.enc_dims[s] : maxdim;
+  void* mel = ar.get(rows * c.n_mels * es);
+  float* x = reinterpret_cast<float*>(ar.get(rows * maxdim * 4));
+  void* a = ar.get(rows * maxdim * es);
+  void* hid = ar.get(rows * maxdim * 4 * es);  // also holds the fp32 stem output before its LayerNorm
+  if (dry) return DC_OK;
+
+  DC_TRY(launch_transpose_ncl_to_nlc(mel_ncl, mel, ad, B, c.n_mels, T, st));
+  {  // stem: Conv1d(128->256, k7, pad 3) + LN channels_first (encoders.py:22-32)
+    Epilogue e;
+    e.out0 = hid;
+    e.out0_dt = DT_F32;
+    DC_TRY(run_dense(h, h->stem, mel, B, T, e, st));
+    DC_TRY(launch_dwconv_ln(reinterpret_cast<const float*>(hid), nullptr, nullptr, h->stem_ln_w, h->stem_ln_b, x,
+                            DT_F32, B, T, c.enc_dims[0], st));
+  }
+  for (int s = 0; s < 4; ++s) {
+    if (s > 0) {  // LN channels_first + Conv1d(k=1) (encoders.py:34-39)
+      DC_TRY(launch_dwconv_ln(x, nullptr, nullptr, h->down_ln_w[s], h->down_ln_b[s], a, ad, B, T, c.enc_dims[s - 1],
+                              st));
+      Epilogue e;
+      e.out0 = x;
+      e.out0_dt = DT_F32;
+      DC_TRY(run_dense(h, h->down_conv[s], a, B, T, e, st));
+    }
+    for (const Block& blk : h->enc_blocks[s]) DC_TRY(run_block(h, blk, x, a, hid, B, T, nullptr, nullptr, false, st));
+  }
+  DC_TRY(launch_dwconv_ln(x, nullptr, nullptr, h->final_ln_w, h->final_ln_b, enc_out, DT_F32, B, T, c.enc_dims[3],
+                          st));
+  return DC_OK;
+}
+
+// project_out + upsample (ConvTranspose1d k1 + ConvNeXtBlock) shared by forward and decode (grfvq.py:109,144)
+static int quantizer_tail(const dc_handle_s* h, const void* fup_op, int B, int T, float* x, void* a, void* hid,
+                          void* qd, float* out_nlc, cudaStream_t st) {
+  const int ad = act_dt(h);
+  Epilogue e;
+  e.out0 = qd;
+  e.out0_dt = ad;
+  DC_TRY(run_dense(h, h->proj_out, fup_op, B, T, e, st));
+  Epilogue e2;
+  e2.out0 = x;
+  e2.out0_dt = DT_F32;
+  DC_TRY(run_dense(h, h->q_up, qd, B, T, e2, st));
+  return run_block(h, h->q_up_blk, x, a, hid, B, T, out_nlc, nullptr, false, st);
+}
+
+static int stage_quantizer(const dc_handle_s* h, const float* enc, int B, int T, int64_t* codes, void* x_pjt_in,
+                           float* fup, float* quantized, Arena& ar, bool dry, cudaStream_t st) {
+  const size_t rows = (size_t)B * T, es = act_es(h);
+  const int ad = act_dt(h), D = h->cfg.enc_dims[3], CD = h->CD;
+  float* x = reinterpret_cast<float*>(ar.get(rows * D * 4));
+  void* a = ar.get(rows * D * es);
+  void* hid = ar.get(rows * D * 4 * es);
+  void* zop = ar.get(rows * D * es);
+  void* qd = ar.get(rows * D * es);
+  void* enc_op = h->mode == DC_MODE_BF16 ? ar.get(rows * D * 2) : nullptr;
+  void* fup_op = (h->mode == DC_MODE_BF16 || !fup) ? ar.get(rows * CD * es) : nullptr;
+  const size_t vq_bytes = vq_workspace_bytes((int64_t)rows, CD, ad == DT_BF16);
+  void* vq_ws = ar.get(vq_bytes);
+  if (dry) return DC_OK;
+
+  const void* a0 = enc;
+  if (h->mode == DC_MODE_BF16) {
+    DC_TRY(launch_cast(enc, reinterpret_cast<__nv_bfloat16*>(enc_op), rows * D, st));
+    a0 = enc_op;
+  }
+  {  // downsample = Conv1d(k=1,s=1) + ConvNeXtBlock (grfvq.py:68-81,107)
+    Epilogue e;
+    e.out0 = x;
+    e.out0_dt = DT_F32;
+    DC_TRY(run_dense(h, h->q_down, a0, B, T, e, st));
+    DC_TRY(run_block(h, h->q_down_blk, x, a, hid, B, T, nullptr, zop, false, st));
+  }
+  {  // project_in (residual_vq.py:152); output dtype = what the reference hands to the codebook
+    Epilogue e;
+    e.out0 = x_pjt_in;
+    e.out0_dt = ad;
+    DC_TRY(run_dense(h, h->proj_in, zop, B, T, e, st));
+  }
+  DC_TRY(launch_vq_search(x_pjt_in, ad, nullptr, (int64_t)rows, CD, h->codebook, h->codebook_bf16, h->c2, h->c2max,
+                          h->K, codes, vq_ws, vq_bytes, h->vq_window, h->vq_tc, h->vq_x2_exact, st, h->sm_count, nullptr));
+  // batched_embedding (vector_quantize_pytorch.py:243-247,506): quantized_fup = codebook rows
+  const void* fop;
+  if (h->mode == DC_MODE_BF16) {
+    DC_TRY(launch_gather_rows(h->codebook, codes, (int64_t)rows, CD, h->K, fup, reinterpret_cast<__nv_bfloat16*>(fup_op), st));
+    fop = fup_op;
+  } else {
+    float* dst = fup ? fup : reinterpret_cast<float*>(fup_op);
+    DC_TRY(launch_gather_rows(h->codebook, codes, (int64_t)rows, CD, h->K, dst, nullptr, st));
+    fop = dst;
+  }
+  return quantizer_tail(h, fop, B, T, x, a, hid, qd, quantized, st);
+}
+
+static int stage_decode_codes(const dc_handle_s* h, const int64_t* codes, int B, int T, float* z_out, Arena& ar,
+                              bool dry, cudaStream_t st) {
+  const size_t rows = (size_t)B * T, es = act_es(h);
+  const int D = h->cfg.enc_dims[3], CD = h->CD;
+  float* x = reinterpret_cast<float*>(ar.get(rows * D * 4));
+  void* a = ar.get(rows * D * es);
+  void* hid = ar.get(rows * D * 4 * es);
+  void* qd = ar.get(rows * D * es);
+  void* fup_op = ar.get(rows * CD * es);
+  if (dry) return DC_OK;
+  if (h->mode == DC_MODE_BF16)
+    DC_TRY(launch_gather_rows(h->codebook, codes, (int64_t)rows, CD, h->K, nullptr,
+                              reinterpret_cast<__nv_bfloat16*>(fup_op), st));
+  else
+    DC_TRY(launch_gather_rows(h->codebook, codes, (int64_t)rows, CD, h->K, reinterpret_cast<float*>(fup_op), nullptr, st));
+  return quantizer_tail(h, fup_op, B, T, x, a, hid, qd, z_out, st);
+}
+
+static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, float* wav, Arena& ar, bool dry,
+                           cudaStream_t st) {
+  const dc_config& c = h->cfg;
+  const size_t es = act_es(h);
+  const int ad = act_dt(h);
+  const int C0 = c.up_initial_channel, Din = h->conv_pre.C;
+  // largest activation (elements per clip) over conv_pre output and every stage
+  size_t max_elems = (size_t)T * C0;
+  {
+    size_t L = T;
+    int C = C0;
+    for (int i = 0; i < c.n_ups; ++i) {
+      L *= c.up_rates[i];
+      C /= 2;
+      max_elems = L * C > max_elems ? L * C : max_elems;
+    }
+  }
+  void* carry[2] = {ar.get((size_t)B * max_elems * es), ar.get((size_t)B * max_elems * es)};
+  void* zop = h->mode == DC_MODE_BF16 ? ar.get((size_t)B * T * Din * 2) : nullptr;
+  const size_t m0 = ar.mark();
+
+  if (!dry) {
+    const void* a0 = z;
+    if (h->mode == DC_MODE_BF16) {
+      DC_TRY(launch_cast(z, reinterpret_cast<__nv_bfloat16*>(zop), (size_t)B * T * Din, st));
+      a0 = zop;
+    }
+    Epilogue e;  // conv_pre (generators.py:121); only silu(x) is consumed downstream (:125)
+    e.out1 = carry[0];
+    e.out1_dt = ad;
+    DC_TRY(run_dense(h, h->conv_pre, a0, B, T, e, st));
+  }
+  int cur = 0;
+  int L = T, C = C0;
+  for (int i = 0; i < c.n_ups; ++i) {
+    const int Lin = L, Cout = C / 2;
+    L = Lin * c.up_rates[i];
+    const size_t n = (size_t)B * L * Cout;
+    ar.release(m0);
+    float* x = reinterpret_cast<float*>(ar.get(n * 4));
+    void* sx = ar.get(n * es);
+    float* X[3] = {reinterpret_cast<float*>(ar.get(n * 4)), reinterpret_cast<float*>(ar.get(n * 4)),
+                   reinterpret_cast<float*>(ar.get(n * 4))};
+    void* sb = ar.get(n * es);
+    void* tb = ar.get(n * es);
+    if (!dry) {
+      {  // silu -> ConvTranspose1d (generators.py:125-126): stride phases stacked along N
+        Epilogue e;
+        e.out0 = x;
+        e.out0_dt = DT_F32;
+        e.out1 = sx;
+        e.out1_dt = ad;
+        DC_TRY(run_dense(h, h->ups[i], carry[cur], B, Lin, e, st));
+      }
+      // ParralelBlock: mean of 3 ResBlock1 (convnext_utils.py:106-113,137-138)
+      for (int b = 0; b < 3; ++b) {
+        const float* cur_x = x;
+        const void* cur_s = sx;
+        for (int n3 = 0; n3 < 3; ++n3) {
+          Epilogue e1;  // xt = silu(c1(silu(x)))
+          e1.act = ACT_SILU;
+          e1.out0 = tb;
+          e1.out0_dt = ad;
+          DC_TRY(run_dense(h, h->rb[i][b][0][n3], cur_s, B, L, e1, st));
+          Epilogue e2;  // x = c2(xt) + x
+          e2.res = cur_x;
+          e2.res_dt = DT_F32;
+          if (n3 < 2) {
+            e2.out0 = X[b];
+            e2.out0_dt = DT_F32;
+            e2.out1 = sb;
+            e2.out1_dt = ad;
+          } else if (b < 2) {
+            e2.out0 = X[b];
+            e2.out0_dt = DT_F32;
+          } else {  // last conv of the last branch: fold the 3-branch mean and the next op's silu
+            e2.add1 = X[0];
+            e2.add2 = X[1];
+            e2.add_dt = DT_F32;
+            e2.scale = 1.f / 3.f;
+            e2.out1 = carry[cur ^ 1];
+            e2.out1_dt = ad;
+          }
+          DC_TRY(run_dense(h, h->rb[i][b][1][n3], tb, B, L, e2, st));
+          cur_x = X[b];
+          cur_s = sb;
+        }
+      }
+    }
+    cur ^= 1;
+    C = Cout;
+  }
+  ar.release(m0);
+  if (!dry)  // silu (folded above) -> conv_post -> tanh (generators.py:141-145)
+    DC_TRY(launch_conv_post_tanh(carry[cur], ad, h->post_w, h->post_b, wav, B, L, st));
+  return DC_OK;
+}
+
+}  // namespace dc
+
+// ================================================================================================ C ABI
+#define DC_API_BEGIN(h)                                                    \
+  DC_CHECK((h) != nullptr, DC_ERR_ARG, "null handle");                     \
+  DC_CUDA(cudaSetDevice((h)->device))
+#define DC_NEED_FINAL(h) DC_CHECK((h)->finalized, DC_ERR_STATE, "call dc_finalize() first")
+
+extern "C" {
+
+int dc_version(void) { return 100; }
+const char* dc_last_error(void) { return g_err; }
+
+int dc_default_config(dc_config* c) {
+  DC_CHECK(c != nullptr, DC_ERR_ARG, "null config");
+  memset(c, 0, sizeof(*c));
+  c->n_mels = 128;
+  const int depths[4] = {3, 3, 9, 3}, dims[4] = {256, 512, 768, 1024};
+  for (int i = 0; i < 4; ++i) {
+    c->enc_depths[i] = depths[i];
+    c->enc_dims[i] = dims[i];
+  }
+  c->codebook_size = 32768;
+  c->codebook_dim = 3584;
+  c->n_ups = 5;
+  const int rates[5] = {8, 4, 2, 2, 2}, ks[5] = {16, 12, 4, 4, 4};
+  for (int i = 0; i < 5; ++i) {
+    c->up_rates[i] = rates[i];
+    c->up_kernels[i] = ks[i];
+  }
+  c->up_initial_channel = 1024;
+  const int rk[3] = {3, 7, 11}, rd[3] = {1, 3, 5};
+  for (int i = 0; i < 3; ++i) {
+    c->rb_kernels[i] = rk[i];
+    c->rb_dilations[i] = rd[i];
+  }
+  c->pre_kernel = 13;
+  c->post_kernel = 13;
+  return DC_OK;
+}
+
+int dc_create(int device, int mode, const dc_config* cfg, dc_handle* out) {
+  DC_CHECK(out != nullptr, DC_ERR_ARG, "null out pointer");
+  DC_CHECK(mode == DC_MODE_FP32 || mode == DC_MODE_BF16, DC_ERR_ARG, "unknown mode %d", mode);
+  int ndev = 0;
+  DC_CUDA(cudaGetDeviceCount(&ndev));
+  DC_CHECK(device >= 0 && device < ndev, DC_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+  cudaDeviceProp prop;
+  DC_CUDA(cudaGetDeviceProperties(&prop, device));
+  DC_CHECK(prop.major == 10, DC_ERR_ARCH, "device %d is sm_%d%d; this library contains only sm_100a code", device,
+           prop.major, prop.minor);
+  DC_CUDA(cudaSetDevice(device));
+  dc_handle_s* h = new dc_handle_s();
+  h->device = device;
+  h->mode = mode;
+  h->sm_count = prop.multiProcessorCount;
+  if (cfg) h->cfg = *cfg;
+  else dc_default_config(&h->cfg);
+  const dc_config& c = h->cfg;
+  bool ok = c.n_ups >= 1 && c.n_ups <= 8 && c.n_mels % 32 == 0;
+  for (int i = 0; i < 4; ++i) ok = ok && c.enc_depths[i] >= 0 && c.enc_dims[i] % 128 == 0 && c.enc_dims[i] <= 1024 && c.enc_dims[i] >= 256;
+  ok = ok && (c.up_initial_channel >> c.n_ups) >= 32 && ((c.up_initial_channel >> c.n_ups) << c.n_ups) == c.up_initial_channel;
+  if (!ok) {
+    delete h;
+    set_error("unsupported configuration (dims must be 256..1024 in steps of 128, 1..8 upsample stages, >= 32 final channels)");
+    return DC_ERR_SHAPE;
+  }
+  *out = h;
+  return DC_OK;
+}
+
+int dc_destroy(dc_handle h) {
+  if (!h) return DC_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->raw)
+    if (kv.second.owned && kv.second.d) cudaFree(kv.second.d);
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+  return DC_OK;
+}
+
+int dc_set_option(dc_handle h, const char* key, double value) {
+  DC_CHECK(h != nullptr && key != nullptr, DC_ERR_ARG, "null argument");
+  if (!strcmp(key, "vq_window")) {
+    DC_CHECK(value > 0.0 && value <= 16.0, DC_ERR_ARG, "vq_window must be in (0, 16]");
+    h->vq_window = (float)value;
+  } else if (!strcmp(key, "vq_tensor_core")) {
+    h->vq_tc = value != 0.0;
+  } else if (!strcmp(key, "vq_x2_exact")) {
+    h->vq_x2_exact = value != 0.0;
+  } else {
+    set_error("unknown option '%s'", key);
+    return DC_ERR_ARG;
+  }
+  return DC_OK;
+}
+
+int dc_set_tensor(dc_handle h, const char* name, const float* data_dev, const int64_t* shape, int ndim) {
+  DC_API_BEGIN(h);
+  DC_CHECK(name && data_dev && shape && ndim >= 0 && ndim <= 4, DC_ERR_ARG, "bad argument to dc_set_tensor");
+  const std::string key(name);
+  // training-only buffers of the codebook (EMA state) are accepted and ignored
+  for (const char* skip : {"_codebook.embed_avg", "_codebook.cluster_size", "_codebook.initted"})
+    if (key.size() >= strlen(skip) && key.compare(key.size() - strlen(skip), strlen(skip), skip) == 0) return DC_OK;
+  RawTensor t;
+  t.numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    DC_CHECK(shape[i] > 0, DC_ERR_SHAPE, "%s: non-positive dimension", name);
+    t.shape.push_back(shape[i]);
+    t.numel *= (size_t)shape[i];
+  }
+  auto it = h->raw.find(key);
+  if (it != h->raw.end() && it->second.owned) cudaFree(it->second.d);
+  const bool is_codebook = key.size() >= 15 && key.compare(key.size() - 15, 15, "_codebook.embed") == 0;
+  if (is_codebook) {
+    DC_CHECK((reinterpret_cast<uintptr_t>(data_dev) & 15) == 0, DC_ERR_ARG, "codebook must be 16-byte aligned");
+    t.d = const_cast<float*>(data_dev);  // referenced in place (470 MB)
+    t.owned = false;
+  } else {
+    void* p = nullptr;
+    DC_CUDA(cudaMalloc(&p, t.numel * 4));
+    DC_CUDA(cudaMemcpy(p, data_dev, t.numel * 4, cudaMemcpyDeviceToDevice));
+    t.d = reinterpret_cast<float*>(p);
+    t.owned = true;
+  }
+  h->raw[key] = t;
+  h->finalized = false;
+  return DC_OK;
+}
+
+int dc_finalize(dc_handle h, void* stream) {
+  DC_API_BEGIN(h);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (void* p : h->owned) cudaFree(p);
+  h->owned.clear();
+  const dc_config& c = h->cfg;
+  char buf[256];
+  const bool has_enc = find_raw(h, "encoder.norm.weight") != nullptr;
+  const bool has_q = find_raw(h, "quantizer.grvq.rvqs.0.project_in.weight") != nullptr;
+  const bool has_gen = find_raw(h, "generator.conv_post.bias") != nullptr;
+  DC_CHECK(has_enc || has_q || has_gen, DC_ERR_STATE, "no weights set");
+
+  if (has_enc) {  // ---- encoder (models/encoders.py:8-61)
+    DC_TRY(pack_conv1d(h, "encoder.downsample_layers.0.0.", 1, &h->stem, st));
+    DC_CHECK(h->stem.C == c.n_mels && h->stem.N == c.enc_dims[0], DC_ERR_SHAPE, "stem conv shape does not match the config");
+    {
+      DC_GET_RAW(w, "encoder.downsample_layers.0.1.weight");
+      DC_GET_RAW(b, "encoder.downsample_layers.0.1.bias");
+      h->stem_ln_w = w->d;
+      h->stem_ln_b = b->d;
+    }
+    for (int s = 1; s < 4; ++s) {
+      snprintf(buf, sizeof(buf), "encoder.downsample_layers.%d.", s);
+      DC_GET_RAW(w, std::string(buf) + "0.weight");
+      DC_GET_RAW(b, std::string(buf) + "0.bias");
+      h->down_ln_w[s] = w->d;
+      h->down_ln_b[s] = b->d;
+      DC_TRY(pack_conv1d(h, std::string(buf) + "1.", 1, &h->down_conv[s], st));
+      DC_CHECK(h->down_conv[s].C == c.enc_dims[s - 1] && h->down_conv[s].N == c.enc_dims[s], DC_ERR_SHAPE,
+               "%s1.weight shape does not match the config", buf);
+    }
+    for (int s = 0; s < 4; ++s) {
+      h->enc_blocks[s].assign(c.enc_depths[s], Block());
+      for (int j = 0; j < c.enc_depths[s]; ++j) {
+        snprintf(buf, sizeof(buf), "encoder.stages.%d.%d.", s, j);
+        DC_TRY(pack_block(h, buf, &h->enc_blocks[s][j], st));
+        DC_CHECK(h->enc_blocks[s][j].C == c.enc_dims[s], DC_ERR_SHAPE, "%s width does not match the config", buf);
+      }
+    }
+    DC_GET_RAW(w, "encoder.norm.weight");
+    DC_GET_RAW(b, "encoder.norm.bias");
+    h->final_ln_w = w->d;
+    h->final_ln_b = b->d;
+  }
+
+  if (has_q) {  // ---- quantizer (vector_quantization/grfvq.py:28-98, utils/residual_vq.py:41-86)
+    const std::string r = "quantizer.grvq.rvqs.0.";
+    DC_TRY(pack_conv1d(h, "quantizer.downsample.0.0.", 1, &h->q_down, st));
+    DC_TRY(pack_block(h, "quantizer.downsample.0.1.", &h->q_down_blk, st));
+    DC_TRY(pack_conv1d(h, r + "project_in.", 1, &h->proj_in, st));
+    DC_TRY(pack_conv1d(h, r + "project_out.", 1, &h->proj_out, st));
+    {
+      DC_GET_RAW(w, "quantizer.upsample.0.0.weight");
+      DC_GET_RAW(b, "quantizer.upsample.0.0.bias");
+      DC_CHECK(w->shape.size() == 3 && w->shape[2] == 1, DC_ERR_SHAPE,
+               "quantizer.upsample.0.0 must be ConvTranspose1d(k=1, s=1) (downsample_factor [1])");
+      DC_TRY(pack_dense(h, w->d, true, (int)w->shape[1], (int)w->shape[0], 1, 1, 0, 1, b->d, &h->q_up, st));
+    }
+    DC_TRY(pack_block(h, "quantizer.upsample.0.1.", &h->q_up_blk, st));
+    DC_GET_RAW(cb, r + "layers.0._codebook.embed");
+    DC_CHECK(cb->shape.size() == 3 && cb->shape[0] == 1, DC_ERR_SHAPE, "codebook must be (1, K, D)");
+    h->K = (int)cb->shape[1];
+    h->CD = (int)cb->shape[2];
+    DC_CHECK(h->CD == h->proj_in.N && h->CD == h->proj_out.C, DC_ERR_SHAPE, "codebook dim does not match project_in/out");
+    DC_CHECK(h->CD % 64 == 0, DC_ERR_SHAPE, "codebook dim must be a multiple of 64");
+    h->codebook = cb->d;
+    DC_TRY(dev_alloc(h, &h->codebook_bf16, (size_t)h->K * h->CD));
+    DC_TRY(dev_alloc(h, &h->c2, (size_t)h->K));
+    DC_TRY(dev_alloc(h, &h->c2max, (size_t)4));
+    DC_TRY(launch_cast(cb->d, h->codebook_bf16, (size_t)h->K * h->CD, st));
+    DC_TRY(launch_row_sqnorm_torch_order(cb->d, h->c2, h->K, h->CD, st));
+    max_reduce_kernel<<<1, 1024, 0, st>>>(h->c2, h->K, h->c2max);
+    ++g_launches_api;
+    DC_CUDA(cudaGetLastError());
+  }
+
+  if (has_gen) {  // ---- generator (models/generators.py:29-116)
+    size_t scratch_elems = 0;
+    for (auto& kv : h->raw)
+      if (kv.first.compare(0, 10, "generator.") == 0 && kv.second.numel > scratch_elems) scratch_elems = kv.second.numel;
+    float* scratch = nullptr;
+    DC_CUDA(cudaMalloc(reinterpret_cast<void**>(&scratch), scratch_elems * 4));
+    int rc = DC_OK;
+    do {
+      rc = pack_wn_conv(h, "generator.conv_pre.", false, 1, (c.pre_kernel - 1) / 2, 1, &h->conv_pre, scratch, st);
+      if (rc) break;
+      int C = c.up_initial_channel;
+      for (int i = 0; i < c.n_ups && rc == DC_OK; ++i) {
+        snprintf(buf, sizeof(buf), "generator.ups.%d.", i);
+        const int k = c.up_kernels[i], u = c.up_rates[i];
+        rc = pack_wn_conv(h, buf, true, u, (k - u) / 2, 1, &h->ups[i], scratch, st);
+        if (rc) break;
+        if (h->ups[i].C != C || h->ups[i].N != u * (C / 2)) {
+          set_error("%s shape does not match the config", buf);
+          rc = DC_ERR_SHAPE;
+          break;
+        }
+        C /= 2;
+        for (int b = 0; b < 3 && rc == DC_OK; ++b)
+          for (int n = 0; n < 3 && rc == DC_OK; ++n) {
+            const int kk = c.rb_kernels[b], d = c.rb_dilations[n];
+            snprintf(buf, sizeof(buf), "generator.resblocks.%d.blocks.%d.convs1.%d.", i, b, n);
+            rc = pack_wn_conv(h, buf, false, 1, (kk * d - d) / 2, d, &h->rb[i][b][0][n], scratch, st);
+            if (rc) break;
+            snprintf(buf, sizeof(buf), "generator.resblocks.%d.blocks.%d.convs2.%d.", i, b, n);
+            rc = pack_wn_conv(h, buf, false, 1, (kk - 1) / 2, 1, &h->rb[i][b][1][n], scratch, st);
+          }
+      }
+      if (rc) break;
+      {  // conv_post: Conv1d(C_last -> 1, k13): folded weight (1, C, k) -> fp32 [k][C]
+        const RawTensor* g = find_raw(h, "generator.conv_post.parametrizations.weight.original0");
+        const RawTensor* v = find_raw(h, "generator.conv_post.parametrizations.weight.original1");
+        const RawTensor* b = find_raw(h, "generator.conv_post.bias");
+        if (!g || !v || !b || v->shape.size() != 3 || v->shape[0] != 1) {
+          set_error("generator.conv_post tensors missing or malformed");
+          rc = DC_ERR_STATE;
+          break;
+        }
+        const int Cl = (int)v->shape[1], k = (int)v->shape[2];
+        if (Cl != 32 || k != 13) {
+          set_error("conv_post must be Conv1d(32 -> 1, k=13); got (%d, k=%d)", Cl, k);
+          rc = DC_ERR_SHAPE;
+          break;
+        }
+        rc = launch_weight_norm_fold(g->d, v->d, scratch, 1, Cl * k, st);
+        if (rc) break;
+        rc = dev_alloc(h, &h->post_w, (size_t)Cl * k);
+        if (rc) break;
+        PackDesc pd;
+        memset(&pd, 0, sizeof(pd));
+        pd.N = 1; pd.J = k; pd.C = Cl; pd.phases = 1; pd.s_n = 0; pd.s_c = k; pd.s_k = 1;
+        for (int j = 0; j < k; ++j) pd.kmap[j] = j;
+        rc = launch_pack_weight(scratch, pd, h->post_w, nullptr, st);
+        if (rc) break;
+        h->post_C = Cl;
+        if (cudaMemcpyAsync(&h->post_b, b->d, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+          set_error("conv_post bias copy failed");
+          rc = DC_ERR_CUDA;
+        }
+      }
+    } while (0);
+    cudaStreamSynchronize(st);
+    cudaFree(scratch);
+    if (rc) return rc;
+  }
+  DC_CUDA(cudaStreamSynchronize(st));
+  // the big raw matrices are no longer needed (1-D parameters stay: kernels read them in place)
+  for (auto it = h->raw.begin(); it != h->raw.end();) {
+    RawTensor& t = it->second;
+    // every >= 2-D tensor (incl. the (C,1,7) depthwise weights) now has a packed copy; a later dc_finalize()
+    // therefore needs the full state_dict again
+    if (t.owned && t.shape.size() >= 2 && t.numel > 4096) {
+      cudaFree(t.d);
+      it = h->raw.erase(it);
+    } else {
+      ++it;
+    }
+  }
+  h->finalized = true;
+  return DC_OK;
+}
+
+static int stage_dispatch(dc_handle h, int stage, int B, int T, Arena& ar, bool dry, const void* in, void* o0, void* o1,
+                          void* o2, void* o3, cudaStream_t st) {
+  switch (stage) {
+    case DC_STAGE_ENCODER:
+      DC_CHECK(h->final_ln_w != nullptr, DC_ERR_STATE, "encoder weights not loaded");
+      return stage_encoder(h, reinterpret_cast<const float*>(in), B, T, reinterpret_cast<float*>(o0), ar, dry, st);
+    case DC_STAGE_QUANTIZER:
+      DC_CHECK(h->codebook != nullptr, DC_ERR_STATE, "quantizer weights not loaded");
+      return stage_quantizer(h, reinterpret_cast<const float*>(in), B, T, reinterpret_cast<int64_t*>(o0), o1,
+                             reinterpret_cast<float*>(o2), reinterpret_cast<float*>(o3), ar, dry, st);
+    case DC_STAGE_DECODE_CODES:
+      DC_CHECK(h->codebook != nullptr, DC_ERR_STATE, "quantizer weights not loaded");
+      return stage_decode_codes(h, reinterpret_cast<const int64_t*>(in), B, T, reinterpret_cast<float*>(o0), ar, dry, st);
+    case DC_STAGE_GENERATOR:
+      DC_CHECK(h->post_w != nullptr, DC_ERR_STATE, "generator weights not loaded");
+      return stage_generator(h, reinterpret_cast<const float*>(in), B, T, reinterpret_cast<float*>(o0), ar, dry, st);
+    default:
+      set_error("unknown stage %d", stage);
+      return DC_ERR_ARG;
+  }
+}
+
+int dc_workspace_bytes(dc_handle h, int stage, int B, int T, size_t* bytes) {
+  DC_CHECK(h != nullptr && bytes != nullptr, DC_ERR_ARG, "null argument");
+  DC_NEED_FINAL(h);
+  DC_CHECK(B > 0 && T > 0, DC_ERR_SHAPE, "B and T must be positive");
+  Arena ar;
+  // a non-null fup pointer makes the fp32-mode plan the smaller one; plan for the larger (fup == NULL)
+  DC_TRY(stage_dispatch(h, stage, B, T, ar, true, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+  *bytes = ar.peak + 1024;
+  return DC_OK;
+}
+
+static int run_stage(dc_handle h, int stage, int B, int T, const void* in, void* o0, void* o1, void* o2, void* o3,
+                     void* ws, size_t ws_bytes, void* stream) {
+  DC_API_BEGIN(h);
+  DC_NEED_FINAL(h);
+  DC_CHECK(B > 0 && T > 0, DC_ERR_SHAPE, "B and T must be positive");
+  DC_CHECK((long long)B * T * 256 < (1ll << 31), DC_ERR_SHAPE, "B*T too large for one call (split the batch)");
+  DC_CHECK(in != nullptr && o0 != nullptr, DC_ERR_ARG, "null tensor pointer");
+  size_t need = 0;
+  DC_TRY(dc_workspace_bytes(h, stage, B, T, &need));
+  DC_CHECK(ws != nullptr && ws_bytes >= need, DC_ERR_WORKSPACE, "workspace %zu < required %zu bytes", ws_bytes, need);
+  Arena ar;
+  ar.base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+  ar.cap = ws_bytes;
+  return stage_dispatch(h, stage, B, T, ar, false, in, o0, o1, o2, o3, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dc_encoder_forward(dc_handle h, const float* mel_ncl_dev, int B, int T, float* enc_nlc_dev, void* ws_dev,
+                       size_t ws_bytes, void* stream) {
+  return run_stage(h, DC_STAGE_ENCODER, B, T, mel_ncl_dev, enc_nlc_dev, nullptr, nullptr, nullptr, ws_dev, ws_bytes, stream);
+}
+
+int dc_quantizer_forward(dc_handle h, const float* enc_nlc_dev, int B, int T, int64_t* codes_dev, void* x_pjt_in_dev,
+                         float* fup_dev, float* quantized_nlc_dev, void* ws_dev, size_t ws_bytes, void* stream) {
+  DC_CHECK(x_pjt_in_dev != nullptr && quantized_nlc_dev != nullptr, DC_ERR_ARG, "null output pointer");
+  return run_stage(h, DC_STAGE_QUANTIZER, B, T, enc_nlc_dev, codes_dev, x_pjt_in_dev, fup_dev, quantized_nlc_dev, ws_dev,
+                   ws_bytes, stream);
+}
+
+int dc_quantizer_decode(dc_handle h, const int64_t* codes_dev, int B, int T, float* z_nlc_dev, void* ws_dev,
+                        size_t ws_bytes, void* stream) {
+  return run_stage(h, DC_STAGE_DECODE_CODES, B, T, codes_dev, z_nlc_dev, nullptr, nullptr, nullptr, ws_dev, ws_bytes, stream);
+}
+
+int dc_generator_forward(dc_handle h, const float* z_nlc_dev, int B, int T, float* wav_dev, void* ws_dev,
+                         size_t ws_bytes, void* stream) {
+  return run_stage(h, DC_STAGE_GENERATOR, B, T, z_nlc_dev, wav_dev, nullptr, nullptr, nullptr, ws_dev, ws_bytes, stream);
+}
+
+int dc_vq_workspace_bytes(dc_handle h, int64_t N, int x_is_bf16, size_t* bytes) {
+  DC_CHECK(h != nullptr && bytes != nullptr, DC_ERR_ARG, "null argument");
+  DC_NEED_FINAL(h);
+  DC_CHECK(h->codebook != nullptr, DC_ERR_STATE, "quantizer weights not loaded");
+  *bytes = vq_workspace_bytes(N, h->CD, x_is_bf16 != 0) + 256;
+  return DC_OK;
+}
+
+int dc_vq_search(dc_handle h, const void* x_dev, int x_is_bf16, const float* x2_dev, int64_t N, int64_t* codes_dev,
+                 void* ws_dev, size_t ws_bytes, void* stream, int* stats_host) {
+  DC_API_BEGIN(h);
+  DC_NEED_FINAL(h);
+  DC_CHECK(h->codebook != nullptr, DC_ERR_STATE, "quantizer weights not loaded");
+  DC_CHECK(x_dev != nullptr && codes_dev != nullptr && N >= 0, DC_ERR_ARG, "bad argument to dc_vq_search");
+  DC_CHECK((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0, DC_ERR_ARG, "x must be 16-byte aligned");
+  char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws_dev) + 255) & ~uintptr_t(255));
+  const size_t lost = ws_dev ? (size_t)(ws - reinterpret_cast<char*>(ws_dev)) : 0;
+  return launch_vq_search(x_dev, x_is_bf16 ? DT_BF16 : DT_F32, x2_dev, N, h->CD, h->codebook, h->codebook_bf16, h->c2,
+                          h->c2max, h->K, codes_dev, ws_dev ? ws : nullptr, ws_bytes > lost ? ws_bytes - lost : 0,
+                          h->vq_window, h->vq_tc, h->vq_x2_exact, reinterpret_cast<cudaStream_t>(stream), h->sm_count,
+                          stats_host);
+}
+
+int dc_ncl_to_nlc(const float* in_dev, float* out_dev, int B, int C, int T, void* stream) {
+  DC_CHECK(in_dev && out_dev && B > 0 && C > 0 && T > 0, DC_ERR_ARG, "bad argument to dc_ncl_to_nlc");
+  return launch_transpose_ncl_to_nlc(in_dev, out_dev, DT_F32, B, C, T, reinterpret_cast<cudaStream_t>(stream));
+}
+int dc_nlc_to_ncl(const float* in_dev, float* out_dev, int B, int T, int C, void* stream) {
+  DC_CHECK(in_dev && out_dev && B > 0 && C > 0 && T > 0, DC_ERR_ARG, "bad argument to dc_nlc_to_ncl");
+  return launch_transpose_nlc_to_ncl(in_dev, out_dev, B, T, C, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- op-level entry points (tests / micro-benchmarks): temporaries are allocated and freed here --------------
+int dc_op_conv_gemm(dc_handle h, const float* a_dev, const float* w_dev, const float* bias_dev, const float* res_dev,
+                    float* out_dev, int B, int T, int C, int J, int shift0, int dil, int N, int act, void* stream) {
+  DC_API_BEGIN(h);
+  DC_CHECK(a_dev && w_dev && out_dev, DC_ERR_ARG, "null tensor pointer");
+  DC_CHECK(B > 0 && T > 0 && C > 0 && J > 0 && N > 0 && dil > 0, DC_ERR_SHAPE, "bad shape");
+  DC_CHECK(act >= ACT_NONE && act <= ACT_SILU, DC_ERR_ARG, "bad activation %d", act);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t na = (size_t)B * T * C, nw = (size_t)N * J * C;
+  Epilogue e;
+  e.bias = bias_dev;
+  e.act = act;
+  e.res = res_dev;
+  e.res_dt = DT_F32;
+  e.out0 = out_dev;
+  e.out0_dt = DT_F32;
+  e.ldo = N;
+  ConvGemmShape s{B, T, C, J, shift0, dil, N};
+  int rc;
+  if (h->mode == DC_MODE_BF16) {
+    __nv_bfloat16 *ab = nullptr, *wb = nullptr;
+    DC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ab), na * 2));
+    if (cudaMalloc(reinterpret_cast<void**>(&wb), nw * 2) != cudaSuccess) {
+      cudaFree(ab);
+      set_error("dc_op_conv_gemm: out of memory");
+      return DC_ERR_CUDA;
+    }
+    rc = launch_cast(a_dev, ab, na, st);
+    if (!rc) rc = launch_cast(w_dev, wb, nw, st);
+    if (!rc) rc = launch_gemm_tc(ab, wb, s, e, st, h->sm_count);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    cudaFree(ab);
+    cudaFree(wb);
+    if (!rc && ce != cudaSuccess) {
+      set_error("dc_op_conv_gemm: %s", cudaGetErrorString(ce));
+      rc = DC_ERR_CUDA;
+    }
+  } else {
+    float* wt = nullptr;
+    DC_CUDA(cudaMalloc(reinterpret_cast<void**>(&wt), nw * 4));
+    PackDesc pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.N = N; pd.J = 1; pd.C = J * C; pd.phases = 1; pd.s_n = (long long)J * C; pd.s_c = 1; pd.s_k = 0;
+    pd.kmap[0] = 0;
+    rc = launch_pack_weight(w_dev, pd, wt, nullptr, st);
+    if (!rc) rc = launch_gemm_f32(a_dev, wt, s, e, st);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    cudaFree(wt);
+    if (!rc && ce != cudaSuccess) {
+      set_error("dc_op_conv_gemm: %s", cudaGetErrorString(ce));
+      rc = DC_ERR_CUDA;
+    }
+  }
+  return rc;
+}
+
+int dc_op_dwconv_ln(dc_handle h, const float* in_dev, const float* dw_w_dev, const float* dw_b_dev,
+                    const float* ln_w_dev, const float* ln_b_dev, float* out_dev, int B, int T, int C, void* stream) {
+  DC_API_BEGIN(h);
+  DC_CHECK(in_dev && ln_w_dev && ln_b_dev && out_dev, DC_ERR_ARG, "null tensor pointer");
+  DC_CHECK(B > 0 && T > 0, DC_ERR_SHAPE, "bad shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* wt = nullptr;
+  int rc = DC_OK;
+  if (dw_w_dev) {
+    DC_CHECK(dw_b_dev != nullptr, DC_ERR_ARG, "depthwise bias missing");
+    DC_CUDA(cudaMalloc(reinterpret_cast<void**>(&wt), (size_t)7 * C * 4));
+    PackDesc pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.N = 1; pd.J = 7; pd.C = C; pd.phases = 1; pd.s_n = 0; pd.s_c = 7; pd.s_k = 1;
+    for (int j = 0; j < 7; ++j) pd.kmap[j] = j;
+    rc = launch_pack_weight(dw_w_dev, pd, wt, nullptr, st);
+  }
+  if (!rc) rc = launch_dwconv_ln(in_dev, wt, dw_b_dev, ln_w_dev, ln_b_dev, out_dev, DT_F32, B, T, C, st);
+  cudaError_t ce = cudaStreamSynchronize(st);
+  if (wt) cudaFree(wt);
+  if (!rc && ce != cudaSuccess) {
+    set_error("dc_op_dwconv_ln: %s", cudaGetErrorString(ce));
+    rc = DC_ERR_CUDA;
+  }
+  return rc;
+}
+
+uint64_t dc_launch_count(void) {
+  return g_launches_api + gemm_tc_launch_count() + gemm_f32_launch_count() + pointwise_launch_count() + vq_launch_count();
+}
+
+}  // extern "C"

@@ -46,7 +46,7 @@ struct ConvGemmShape {
 
 // Runtime epilogue, applied per output element v = acc:
 //   v += bias[n]; v = act(v); v *= gamma[n]; v += res[row, n]; if (add1) v = (v + add1 + add2) * scale;
-//   out0[row, n] = v;  out1[row, n] = silu(v)
+//   out0[row, n] = v;  out1[row, n] = out1_silu ? silu(v) : v
 // row = b*T + t, all row-major with pitch ldo.
 struct Epilogue {
   const float* bias = nullptr;
@@ -60,6 +60,7 @@ struct Epilogue {
   int res_dt = DT_F32, add_dt = DT_BF16, out0_dt = DT_F32, out1_dt = DT_BF16;
   int ldo = 0;
   float scale = 1.f;
+  int out1_silu = 1;
 };
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
@@ -84,7 +85,7 @@ __device__ __forceinline__ void epilogue_store(const Epilogue& e, size_t row, in
   if (e.res) v += ld_as_f32(e.res, o, e.res_dt);
   if (e.add1) v = (v + ld_as_f32(e.add1, o, e.add_dt) + ld_as_f32(e.add2, o, e.add_dt)) * e.scale;
   if (e.out0) st_from_f32(e.out0, o, e.out0_dt, v);
-  if (e.out1) st_from_f32(e.out1, o, e.out1_dt, silu_f(v));
+  if (e.out1) st_from_f32(e.out1, o, e.out1_dt, e.out1_silu ? silu_f(v) : v);
 }
 
 // ---------------------------------------------------------------- launchers implemented across the .cu files
@@ -119,12 +120,15 @@ int launch_pack_weight(const float* src, const PackDesc& d, float* out_kn_f32 /*
 int launch_row_sqnorm(const float* in, float* out, int64_t rows, int D, cudaStream_t st);
 
 // VQ (vq.cu)
-struct VqWorkspace;
-size_t vq_workspace_bytes(int64_t nrows, int codebook_size);
-int launch_vq_search(const void* x, int x_dt, const __nv_bfloat16* x_bf16, const float* x2_opt, int64_t nrows, int D,
-                     const float* codebook_f32, const __nv_bfloat16* codebook_bf16, const float* c2, float c2max,
-                     int codebook_size, int64_t* codes, void* ws, size_t ws_bytes, float window_factor,
-                     bool use_tc, cudaStream_t st, int sm_count, int* stats_host_opt);
+size_t vq_workspace_bytes(int64_t nrows, int D, bool x_is_bf16);
+int launch_vq_search(const void* x, int x_dt, const float* x2_opt, int64_t nrows, int D, const float* codebook_f32,
+                     const __nv_bfloat16* codebook_bf16, const float* c2, const float* c2max_dev, int K,
+                     int64_t* codes, void* ws, size_t ws_bytes, float window_factor, bool use_tc, bool x2_exact,
+                     cudaStream_t st, int sm_count, int* stats_host_opt);
+int launch_row_sqnorm_torch_order(const float* in, float* out, int64_t rows, int D, cudaStream_t st);
+uint64_t vq_launch_count();
+uint64_t pointwise_launch_count();
+uint64_t gemm_f32_launch_count();
 
 int sm_count_of_current_device();
 

@@ -150,8 +150,10 @@ __device__ __forceinline__ void epilogue32(const Epilogue& e, size_t row, int n,
   }
   if (e.out0) store32(e.out0, off, e.out0_dt, v);
   if (e.out1) {
+    if (e.out1_silu) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+      for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+    }
     store32(e.out1, off, e.out1_dt, v);
   }
 }

@@ -51,9 +51,32 @@ typedef enum { DC_STAGE_ENCODER = 0, DC_STAGE_QUANTIZER = 1, DC_STAGE_DECODE_COD
 int dc_version(void);
 const char* dc_last_error(void);
 
-/* Lifetime.  Replaces module construction + `.to(device)` (distil_codec.py:52-54, 72-75). */
-int dc_create(int device, int mode, dc_handle* out);
+/* Architecture hyper-parameters: the fields of configs/model_config.json the hot path depends on
+ * (`encoder`, `quantizer`, `decoder` sections; consumed at distil_codec.py:46-54). */
+typedef struct {
+  int n_mels;             /* encoder.input_channels                128 */
+  int enc_depths[4];      /* encoder.depths                        3,3,9,3 */
+  int enc_dims[4];        /* encoder.dims                          256,512,768,1024 */
+  int codebook_size;      /* quantizer.codebook_size               32768 */
+  int codebook_dim;       /* quantizer.codebook_dim                3584 */
+  int n_ups;              /* len(decoder.upsample_rates)           5 */
+  int up_rates[8];        /* decoder.upsample_rates                8,4,2,2,2 */
+  int up_kernels[8];      /* decoder.upsample_kernel_sizes         16,12,4,4,4 */
+  int up_initial_channel; /* decoder.upsample_initial_channel      1024 */
+  int rb_kernels[3];      /* decoder.resblock_kernel_sizes         3,7,11 */
+  int rb_dilations[3];    /* decoder.resblock_dilation_sizes[*]    1,3,5 */
+  int pre_kernel;         /* decoder.pre_conv_kernel_size          13 */
+  int post_kernel;        /* decoder.post_conv_kernel_size         13 */
+} dc_config;
+int dc_default_config(dc_config* cfg);
+
+/* Lifetime.  Replaces module construction + `.to(device)` (distil_codec.py:52-54, 72-75).  cfg NULL = defaults. */
+int dc_create(int device, int mode, const dc_config* cfg, dc_handle* out);
 int dc_destroy(dc_handle h);
+/* Tunables: "vq_window" (fraction of the rigorous bf16 error bound used as the candidate window, default 0.25;
+ * 1.0 = rigorous), "vq_tensor_core" (1 = tcgen05 scorer [default], 0 = CUDA-core scorer), "vq_x2_exact"
+ * (0 [default] = ||x||^2 summed in the order of the reference's CPU path, ATen cascade_sum; 1 = correctly rounded). */
+int dc_set_option(dc_handle h, const char* key, double value);
 
 /* Weight ingestion.  Replaces `load_state_dict` on the three modules (distil_codec.py:91-94): call once per
  * state_dict entry with the reference's key (prefixed `encoder.` / `quantizer.` / `generator.`), an fp32 device
@@ -88,11 +111,13 @@ int dc_quantizer_forward(dc_handle h, const float* enc_nlc_dev, int B, int T, in
  * all in fp32 like the reference, with x.c_j evaluated exactly (fp64) then rounded to fp32.
  *   x_dev    : (N, 3584) rows, dtype x_is_bf16 ? bf16 : fp32
  *   x2_dev   : optional fp32 (N) row square-norms as the caller's reference computes them (strict parity with
- *              a particular reduction order); NULL = correctly rounded exact sum
- *   stats_host : optional int[4] {rows, rescored candidates, rows sent to the exhaustive pass, 0}; forces a sync */
+ *              a particular reduction order, e.g. a CUDA reference); NULL = computed here in the summation order
+ *              of the reference's CPU path (`(x ** 2).sum(-1)`, ATen cascade_sum), see option "vq_x2_exact"
+ *   stats_host : optional int[4] {rows, exactly re-scored candidates, rows sent to the exhaustive pass, rows decided
+ *                without re-scoring}; forces a stream synchronisation */
 int dc_vq_search(dc_handle h, const void* x_dev, int x_is_bf16, const float* x2_dev, int64_t N, int64_t* codes_dev,
                  void* ws_dev, size_t ws_bytes, void* stream, int* stats_host);
-int dc_vq_workspace_bytes(dc_handle h, int64_t N, size_t* bytes);
+int dc_vq_workspace_bytes(dc_handle h, int64_t N, int x_is_bf16, size_t* bytes);
 
 /* quantizer.decode(indices): DownsampleGRVQ.decode, grfvq.py:141-146 -> get_output_from_indices,
  * utils/residual_vq.py:301-303,135-138 (call sites distil_codec.py:591,630).

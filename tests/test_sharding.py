@@ -1,0 +1,76 @@
+"""Host-side clip sharding: partition properties and the N>1 gather over gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from distilcodec_nabeel_b200.sharding import gather_by_clip, run_sharded, shard_clips, shard_sizes
+
+
+@pytest.mark.parametrize("n,ws", [(0, 1), (1, 1), (1, 8), (7, 2), (256, 8), (1000, 8), (5, 3)])
+def test_partition_is_contiguous_balanced_and_complete(n, ws):
+    shards = [shard_clips(n, ws, r) for r in range(ws)]
+    flat = [i for s in shards for i in s]
+    assert flat == list(range(n))
+    sizes = [len(s) for s in shards]
+    assert max(sizes) - min(sizes) <= 1 and sizes == shard_sizes(n, ws)
+
+
+def test_bad_arguments():
+    with pytest.raises(ValueError):
+        shard_clips(4, 0, 0)
+    with pytest.raises(ValueError):
+        shard_clips(4, 2, 2)
+    with pytest.raises(ValueError):
+        shard_clips(-1, 2, 0)
+
+
+def test_single_process_gather_is_identity():
+    x = torch.arange(12).reshape(4, 3)
+    assert gather_by_clip(x, 4) is x
+    with pytest.raises(ValueError):
+        gather_by_clip(x, 5)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, ws, port, n_clips, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        clips = [torch.full((3,), float(i)) for i in range(n_clips)]
+        idx, res = run_sharded(lambda c: c * 2 + 1, clips, ws, rank)           # the per-clip "hot path"
+        local = torch.stack(res) if res else torch.empty(0, 3)
+        full = gather_by_clip(local, n_clips)
+        only0 = gather_by_clip(local, n_clips, dst=0)
+        codes = gather_by_clip(torch.tensor(idx, dtype=torch.int64).reshape(-1, 1), n_clips)
+        q.put((rank, full.tolist(), None if only0 is None else only0.tolist(), codes.flatten().tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_clips", [5, 8])
+def test_world_size_2_gloo_gather_restores_input_order(n_clips):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_clips, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = [[2.0 * i + 1] * 3 for i in range(n_clips)]
+    for rank, full, only0, codes in results:
+        assert full == expect                      # unsharded result, bit for bit, on every rank
+        assert codes == list(range(n_clips))
+        assert (only0 == expect) if rank == 0 else (only0 is None)
