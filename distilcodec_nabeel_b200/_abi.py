@@ -25,6 +25,12 @@ class DcConfig(C.Structure):
                 ("post_kernel", C.c_int)]
 
 
+class DcProfileRow(C.Structure):
+    """dc_profile_row: per-kernel-class device time and algorithmic work."""
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_uint64), ("ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 
 # name -> (restype, argtypes); must list every symbol include/distilcodec_b200.h declares
@@ -48,6 +54,8 @@ SIGNATURES = {
     "dc_nlc_to_ncl": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "dc_op_conv_gemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dc_op_dwconv_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "dc_profile_enable": (_i, [_i]),
+    "dc_profile_collect": (_i, [C.POINTER(DcProfileRow), _i, C.POINTER(_i)]),
     "dc_launch_count": (C.c_uint64, []),
 }
 

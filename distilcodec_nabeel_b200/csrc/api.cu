@@ -36,6 +36,41 @@ int sm_count_of_current_device() {
   return n;
 }
 
+// ---------------------------------------------------------------------------------------------- profiler
+static const char* kProfNames[PC_COUNT] = {"gemm_tc", "gemm_f32", "vq_score", "vq_prep", "vq_rescore",
+                                           "vq_exhaustive", "dwconv_ln", "layernorm", "cast", "gather",
+                                           "transpose", "conv_post_tanh", "prepack"};
+struct ProfRec {
+  int cls;
+  cudaEvent_t e0, e1;
+  double flops, bytes;
+};
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec> g_prof_recs;
+static thread_local std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+ProfScope::ProfScope(int cls, double flops, double bytes, cudaStream_t stream) : st(stream) {
+  if (!g_prof_on) return;
+  ProfRec r{cls, prof_event(), prof_event(), flops, bytes};
+  if (!r.e0 || !r.e1) return;
+  cudaEventRecord(r.e0, st);
+  idx = (int)g_prof_recs.size();
+  g_prof_recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(g_prof_recs[idx].e1, st);
+}
+
 // ---------------------------------------------------------------------------------------------- small kernels
 static thread_local uint64_t g_launches_api = 0;
 
@@ -67,6 +102,7 @@ struct RawTensor {
 
 struct Dense {  // one shifted-row implicit GEMM layer
   int C = 0, J = 1, shift0 = 0, dil = 1, N = 0;
+  float alg_scale = 1.f;            // true MACs / executed MACs (ConvTranspose1d phase GEMMs pad taps with zeros)
   __nv_bfloat16* w_bf16 = nullptr;  // [N][J*C]   (DC_MODE_BF16)
   float* w_f32 = nullptr;           // [J*C][N]   (DC_MODE_FP32)
   const float* bias = nullptr;      // [N]
@@ -179,6 +215,7 @@ static int pack_dense(dc_handle_s* h, const float* src, bool transposed, int O, 
           sh_max = sh > sh_max ? sh : sh_max;
         }
     d->J = sh_max - sh_min + 1;
+    d->alg_scale = (float)k / (float)(stride * d->J);
     d->shift0 = sh_min;
     d->dil = 1;
     d->N = stride * O;
@@ -207,6 +244,7 @@ static int pack_dense(dc_handle_s* h, const float* src, bool transposed, int O, 
   if (bias && transposed && stride > 1) {
     float* b = nullptr;
     DC_TRY(dev_alloc(h, &b, (size_t)d->N));
+    ProfScope ps(PC_PREPACK, 0, 0, st);
     tile_bias_kernel<<<(d->N + 255) / 256, 256, 0, st>>>(bias, b, O, stride);
     ++g_launches_api;
     DC_CUDA(cudaGetLastError());
@@ -267,7 +305,7 @@ static int pack_block(dc_handle_s* h, const std::string& p, Block* blk, cudaStre
 
 // ---- layer runners --------------------------------------------------------------------------------------
 static int run_dense(const dc_handle_s* h, const Dense& d, const void* A, int B, int T, Epilogue ep, cudaStream_t st) {
-  ConvGemmShape s{B, T, d.C, d.J, d.shift0, d.dil, d.N};
+  ConvGemmShape s{B, T, d.C, d.J, d.shift0, d.dil, d.N, d.alg_scale};
   if (!ep.bias) ep.bias = d.bias;
   ep.ldo = d.N;
   if (h->mode == DC_MODE_BF16)
@@ -723,7 +761,10 @@ int dc_finalize(dc_handle h, void* stream) {
     DC_TRY(dev_alloc(h, &h->c2max, (size_t)4));
     DC_TRY(launch_cast(cb->d, h->codebook_bf16, (size_t)h->K * h->CD, st));
     DC_TRY(launch_row_sqnorm_torch_order(cb->d, h->c2, h->K, h->CD, st));
-    max_reduce_kernel<<<1, 1024, 0, st>>>(h->c2, h->K, h->c2max);
+    {
+      ProfScope ps(PC_PREPACK, 0, 0, st);
+      max_reduce_kernel<<<1, 1024, 0, st>>>(h->c2, h->K, h->c2max);
+    }
     ++g_launches_api;
     DC_CUDA(cudaGetLastError());
   }
@@ -898,7 +939,12 @@ int dc_vq_search(dc_handle h, const void* x_dev, int x_is_bf16, const float* x2_
   DC_API_BEGIN(h);
   DC_NEED_FINAL(h);
   DC_CHECK(h->codebook != nullptr, DC_ERR_STATE, "quantizer weights not loaded");
-  DC_CHECK(x_dev != nullptr && codes_dev != nullptr && N >= 0, DC_ERR_ARG, "bad argument to dc_vq_search");
+  DC_CHECK(N >= 0, DC_ERR_ARG, "dc_vq_search: negative row count");
+  if (N == 0) {  // empty batch: nothing to do (empty tensors have null data pointers)
+    if (stats_host) stats_host[0] = stats_host[1] = stats_host[2] = stats_host[3] = 0;
+    return DC_OK;
+  }
+  DC_CHECK(x_dev != nullptr && codes_dev != nullptr, DC_ERR_ARG, "bad argument to dc_vq_search");
   DC_CHECK((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0, DC_ERR_ARG, "x must be 16-byte aligned");
   char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws_dev) + 255) & ~uintptr_t(255));
   const size_t lost = ws_dev ? (size_t)(ws - reinterpret_cast<char*>(ws_dev)) : 0;
@@ -997,6 +1043,48 @@ int dc_op_dwconv_ln(dc_handle h, const float* in_dev, const float* dw_w_dev, con
     set_error("dc_op_dwconv_ln: %s", cudaGetErrorString(ce));
     rc = DC_ERR_CUDA;
   }
+  return rc;
+}
+
+int dc_profile_enable(int on) {
+  for (ProfRec& r : g_prof_recs) {
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  g_prof_recs.clear();
+  g_prof_on = on != 0;
+  return DC_OK;
+}
+
+int dc_profile_collect(dc_profile_row* rows, int cap, int* n) {
+  DC_CHECK(rows != nullptr && n != nullptr && cap >= 0, DC_ERR_ARG, "bad argument to dc_profile_collect");
+  dc_profile_row agg[PC_COUNT];
+  memset(agg, 0, sizeof(agg));
+  int rc = DC_OK;
+  for (ProfRec& r : g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) {
+      set_error("dc_profile_collect: event timing failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = DC_ERR_CUDA;
+    }
+    agg[r.cls].launches += 1;
+    agg[r.cls].ms += ms;
+    agg[r.cls].flops += r.flops;
+    agg[r.cls].bytes += r.bytes;
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  g_prof_recs.clear();
+  int k = 0;
+  for (int c = 0; c < PC_COUNT; ++c) {
+    if (!agg[c].launches) continue;
+    if (k < cap) {
+      rows[k] = agg[c];
+      strncpy(rows[k].name, kProfNames[c], sizeof(rows[k].name) - 1);
+    }
+    ++k;
+  }
+  *n = k;
   return rc;
 }
 

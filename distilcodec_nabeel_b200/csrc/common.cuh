@@ -42,6 +42,7 @@ enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
 // A is channels-last (B, T, C); rows outside [0, T) read as zero (= the conv's zero padding).
 struct ConvGemmShape {
   int B, T, C, J, shift0, dil, N;
+  float alg_scale = 1.f;  // algorithmic / executed MACs (< 1 for ConvTranspose1d phase GEMMs with zero-padded taps)
 };
 
 // Runtime epilogue, applied per output element v = acc:
@@ -131,5 +132,19 @@ uint64_t pointwise_launch_count();
 uint64_t gemm_f32_launch_count();
 
 int sm_count_of_current_device();
+
+// ---------------------------------------------------------------- per-kernel-class timing (bench.py's roofline)
+// Thread-local and off by default.  When enabled (dc_profile_enable) every launcher brackets its kernel with a
+// CUDA event pair on the launching stream and books the launch's ALGORITHMIC flops / HBM bytes.
+enum ProfClass {
+  PC_GEMM_TC = 0, PC_GEMM_F32, PC_VQ_SCORE, PC_VQ_PREP, PC_VQ_RESCORE, PC_VQ_EXHAUSTIVE, PC_DWCONV_LN, PC_LAYERNORM,
+  PC_CAST, PC_GATHER, PC_TRANSPOSE, PC_CONV_POST, PC_PREPACK, PC_COUNT
+};
+struct ProfScope {
+  int idx = -1;
+  cudaStream_t st;
+  ProfScope(int cls, double flops, double bytes, cudaStream_t stream);
+  ~ProfScope();
+};
 
 }  // namespace dc

@@ -107,6 +107,9 @@ int launch_gemm_f32(const float* A, const float* W, const ConvGemmShape& s_in, c
   const int tiles_per_clip = (s.T + 127) / 128;
   const long long mt = (long long)s.B * tiles_per_clip;
   DC_CHECK(mt > 0 && mt < (1ll << 31), DC_ERR_SHAPE, "gemm_f32: bad tile count");
+  const double rows = (double)s.B * s.T;
+  ProfScope ps(PC_GEMM_F32, 2.0 * rows * s.N * s.J * s.C * s.alg_scale,
+               rows * s.C * 4.0 + (double)s.N * s.J * s.C * 4.0 + rows * s.N * 4.0, st);
   if (s.N % 64 == 0) {
     dim3 grid((unsigned)mt, s.N / 64);
     gemm_f32_kernel<64><<<grid, 256, 0, st>>>(A, W, s, e, tiles_per_clip);

@@ -341,8 +341,14 @@ static int launch_cfg(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
   }
   const long long total = m_tiles * n_tiles;
   const int grid = (int)(total < sm_count ? total : sm_count);
-  gemm_tc_kernel<BN, BK, STAGES><<<grid, kGemmThreads, L::TOTAL, st>>>(tmA, tmB, s, e, tiles_per_clip, (int)m_tiles,
-                                                                      n_tiles);
+  {
+    const double rows = (double)s.B * s.T;
+    const double macs = rows * s.N * s.J * s.C * s.alg_scale;
+    // operands once: A rows x C, W, output rows x N (4 B/elt upper bound is not assumed: count bf16 A/W, 4 B out)
+    ProfScope ps(PC_GEMM_TC, 2.0 * macs, rows * s.C * 2.0 + (double)s.N * s.J * s.C * 2.0 + rows * s.N * 4.0, st);
+    gemm_tc_kernel<BN, BK, STAGES><<<grid, kGemmThreads, L::TOTAL, st>>>(tmA, tmB, s, e, tiles_per_clip, (int)m_tiles,
+                                                                        n_tiles);
+  }
   ++g_launches_tc;
   DC_CUDA(cudaGetLastError());
   return DC_OK;

@@ -38,6 +38,7 @@ __global__ void transpose_ncl_to_nlc_kernel(const float* __restrict__ in, TOut* 
 
 int launch_transpose_ncl_to_nlc(const float* in, void* out, int out_dt, int B, int C, int T, cudaStream_t st) {
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  ProfScope ps(PC_TRANSPOSE, 0, (double)B * C * T * (4.0 + (out_dt == DT_F32 ? 4.0 : 2.0)), st);
   if (out_dt == DT_F32) transpose_ncl_to_nlc_kernel<float><<<grid, block, 0, st>>>(in, (float*)out, C, T);
   else transpose_ncl_to_nlc_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(in, (__nv_bfloat16*)out, C, T);
   ++g_launches_pw;
@@ -47,6 +48,7 @@ int launch_transpose_ncl_to_nlc(const float* in, void* out, int out_dt, int B, i
 int launch_transpose_nlc_to_ncl(const float* in, float* out, int B, int T, int C, cudaStream_t st) {
   // (B,T,C) -> (B,C,T) is the same kernel with the roles of C and T swapped
   dim3 grid((C + 31) / 32, (T + 31) / 32, B), block(32, 8);
+  ProfScope ps(PC_TRANSPOSE, 0, (double)B * C * T * 8.0, st);
   transpose_ncl_to_nlc_kernel<float><<<grid, block, 0, st>>>(in, out, T, C);
   ++g_launches_pw;
   DC_CUDA(cudaGetLastError());
@@ -130,6 +132,8 @@ static int dwconv_ln_dispatch(const float* in, const float* dw_w, const float* d
                               const float* ln_b, void* out, int out_dt, int B, int T, cudaStream_t st) {
   const long long rows = (long long)B * T;
   const unsigned grid = (unsigned)((rows + 7) / 8);
+  constexpr int C = VPL * 128;
+  ProfScope ps(dw_w ? PC_DWCONV_LN : PC_LAYERNORM, 0, (double)rows * C * (4.0 + (out_dt == DT_F32 ? 4.0 : 2.0)), st);
   if (dw_w) {
     if (out_dt == DT_F32) dwconv_ln_kernel<VPL, true, float><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (float*)out, B, T);
     else dwconv_ln_kernel<VPL, true, __nv_bfloat16><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (__nv_bfloat16*)out, B, T);
@@ -172,6 +176,7 @@ int launch_cast(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st) 
   if (n4 == 0) return DC_OK;
   unsigned grid = (unsigned)((n4 + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
+  ProfScope ps(PC_CAST, 0, (double)n * 6.0, st);
   cast_kernel<<<grid, 256, 0, st>>>((const float4*)in, (uint2*)out, n4);
   ++g_launches_pw;
   DC_CUDA(cudaGetLastError());
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
 int launch_gather_rows(const float* table, const int64_t* idx, int64_t nrows, int D, int64_t table_rows, float* o32,
                        __nv_bfloat16* o16, cudaStream_t st) {
   if (nrows == 0) return DC_OK;
+  ProfScope ps(PC_GATHER, 0, (double)nrows * D * (4.0 + (o32 ? 4.0 : 0.0) + (o16 ? 2.0 : 0.0)), st);
   gather_rows_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(table, idx, nrows, D, table_rows, o32, o16);
   ++g_launches_pw;
   DC_CUDA(cudaGetLastError());
@@ -246,6 +252,7 @@ __global__ void __launch_bounds__(256) conv_post_tanh_kernel(const TIn* __restri
 int launch_conv_post_tanh(const void* in, int in_dt, const float* w, float bias, float* out, int B, int L,
                           cudaStream_t st) {
   dim3 grid((L + 255) / 256, B);
+  ProfScope ps(PC_CONV_POST, 2.0 * B * (double)L * 32 * 13, (double)B * L * (32.0 * (in_dt == DT_F32 ? 4 : 2) + 4.0), st);
   if (in_dt == DT_F32) conv_post_tanh_kernel<float><<<grid, 256, 0, st>>>((const float*)in, w, bias, out, L);
   else conv_post_tanh_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, w, bias, out, L);
   ++g_launches_pw;
@@ -275,6 +282,7 @@ __global__ void weight_norm_fold_kernel(const float* __restrict__ g, const float
   for (int k = threadIdx.x; k < inner; k += blockDim.x) w[(size_t)i * inner + k] = vi[k] * scale;
 }
 int launch_weight_norm_fold(const float* g, const float* v, float* w, int dim0, int inner, cudaStream_t st) {
+  ProfScope ps(PC_PREPACK, 0, 0, st);
   weight_norm_fold_kernel<<<dim0, 256, 0, st>>>(g, v, w, inner);
   ++g_launches_pw;
   DC_CUDA(cudaGetLastError());
@@ -300,6 +308,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, PackDesc d, fl
 }
 int launch_pack_weight(const float* src, const PackDesc& d, float* o_kn, __nv_bfloat16* o_nk, cudaStream_t st) {
   DC_CHECK(d.phases * d.J <= 8 * 16, DC_ERR_SHAPE, "pack_weight: tap table too large");
+  ProfScope ps(PC_PREPACK, 0, 0, st);
   pack_weight_kernel<<<148 * 8, 256, 0, st>>>(src, d, o_kn, o_nk);
   ++g_launches_pw;
   DC_CUDA(cudaGetLastError());
@@ -324,6 +333,7 @@ __global__ void __launch_bounds__(256) row_sqnorm_kernel(const float* __restrict
 }
 int launch_row_sqnorm(const float* in, float* out, int64_t rows, int D, cudaStream_t st) {
   if (rows == 0) return DC_OK;
+  ProfScope ps(PC_PREPACK, 0, 0, st);
   row_sqnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(in, out, rows, D);
   ++g_launches_pw;
   DC_CUDA(cudaGetLastError());

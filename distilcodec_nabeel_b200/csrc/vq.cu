@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(256) vq_row_sqnorm_kernel(const float* __restr
 int launch_row_sqnorm_torch_order(const float* in, float* out, int64_t rows, int D, cudaStream_t st) {
   if (rows == 0) return DC_OK;
   DC_CHECK(D % 32 == 0, DC_ERR_SHAPE, "row_sqnorm: D=%d must be a multiple of 32", D);
+  ProfScope ps(PC_PREPACK, 0, 0, st);
   vq_row_sqnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(in, out, rows, D);
   ++g_launches_vq;
   DC_CUDA(cudaGetLastError());
@@ -626,16 +627,22 @@ int launch_vq_search(const void* x, int x_dt, const float* x2_opt, int64_t nrows
   const __nv_bfloat16* xb = xb16 ? reinterpret_cast<const __nv_bfloat16*>(x) : w.xb;
   const unsigned row_blocks = (unsigned)((nrows + 7) / 8);
 
+  {
+  ProfScope ps(PC_VQ_PREP, 0, (double)nrows * D * (xb16 ? 2.0 : 6.0), st);
   if (xb16)
     vq_prep_kernel<true><<<row_blocks, 256, 0, st>>>(x, w.xb, w.x2e, w.win, c2max_dev, nrows, D, window_factor,
                                                      x2_exact ? 1 : 0, w.counters);
   else
     vq_prep_kernel<false><<<row_blocks, 256, 0, st>>>(x, w.xb, w.x2e, w.win, c2max_dev, nrows, D, window_factor,
                                                       x2_exact ? 1 : 0, w.counters);
+  }
   ++g_launches_vq;
   DC_CUDA(cudaGetLastError());
 
   int NS = 1;
+  {
+  // algorithmic work of the distance contraction: 2 * N * K * D flops; operands once: x (bf16) + codebook (bf16)
+  ProfScope ps(PC_VQ_SCORE, 2.0 * (double)nrows * K * D, ((double)nrows + K) * D * 2.0, st);
   if (use_tc && K % VQ_BN == 0) {
     const int n_mblk = (int)((nrows + VQ_BM - 1) / VQ_BM);
     const int n_tiles = K / VQ_BN;
@@ -680,19 +687,24 @@ int launch_vq_search(const void* x, int x_dt, const float* x2_opt, int64_t nrows
     vq_score_simt_kernel<<<(unsigned)nrows, 256, (size_t)D * 4, st>>>(xb, codebook_bf16, c2, w.win, w.best, w.cnt,
                                                                        w.cand, (int)nrows, K, D);
   }
+  }
   ++g_launches_vq;
   DC_CUDA(cudaGetLastError());
 
   const float* x2 = x2_opt ? x2_opt : w.x2e;
+  {
+  ProfScope ps(PC_VQ_RESCORE, 0, 0, st);
   if (xb16)
     vq_rescore_kernel<true><<<row_blocks, 256, 0, st>>>(x, x2, codebook_f32, c2, w.win, w.best, w.cnt, w.cand, nrows, D,
                                                          NS, codes, w.ovf_rows, w.counters);
   else
     vq_rescore_kernel<false><<<row_blocks, 256, 0, st>>>(x, x2, codebook_f32, c2, w.win, w.best, w.cnt, w.cand, nrows,
                                                           D, NS, codes, w.ovf_rows, w.counters);
+  }
   ++g_launches_vq;
   DC_CUDA(cudaGetLastError());
 
+  ProfScope ps_ex(PC_VQ_EXHAUSTIVE, 0, 0, st);
   vq_exhaustive_init_kernel<<<32, 256, 0, st>>>(w.ovf_keys, w.counters);
   const int ex_grid = K >= 128 * 8 ? 128 : (K + 7) / 8;
   if (xb16)

@@ -273,5 +273,17 @@ class Engine:
             _abi.check(self.lib.dc_ncl_to_nlc(x.data_ptr(), out.data_ptr(), B, Cc, T, self._stream()), "dc_ncl_to_nlc")
         return out
 
+    def profile(self, on: bool) -> None:
+        """Bracket every kernel launch of this thread with CUDA events (roofline reports); see `profile_rows`."""
+        _abi.check(self.lib.dc_profile_enable(int(on)), "dc_profile_enable")
+
+    def profile_rows(self):
+        """-> [{name, launches, ms, flops, bytes}] per kernel class since `profile(True)`; clears the records."""
+        rows = (_abi.DcProfileRow * 32)()
+        n = C.c_int()
+        _abi.check(self.lib.dc_profile_collect(rows, 32, C.byref(n)), "dc_profile_collect")
+        return [{"name": rows[i].name.decode(), "launches": int(rows[i].launches), "ms": rows[i].ms,
+                 "flops": rows[i].flops, "bytes": rows[i].bytes} for i in range(min(n.value, 32))]
+
     def launch_count(self) -> int:
         return int(self.lib.dc_launch_count())

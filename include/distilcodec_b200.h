@@ -147,6 +147,20 @@ int dc_op_conv_gemm(dc_handle h, const float* a_dev, const float* w_dev, const f
 int dc_op_dwconv_ln(dc_handle h, const float* in_dev, const float* dw_w_dev, const float* dw_b_dev,
                     const float* ln_w_dev, const float* ln_b_dev, float* out_dev, int B, int T, int C, void* stream);
 
+/* Per-kernel-class device timing for roofline reports (thread-local, off by default).  While enabled, every kernel
+ * launch is bracketed by a CUDA event pair on its stream and booked with its ALGORITHMIC flops and HBM bytes.
+ * dc_profile_collect synchronises the recorded events, returns one row per kernel class that launched and clears
+ * the records. */
+typedef struct {
+  char name[32];     /* kernel class, e.g. "gemm_tc", "vq_score", "dwconv_ln" */
+  uint64_t launches;
+  double ms;         /* sum of event-pair durations */
+  double flops;      /* algorithmic FLOPs (2 x MACs of the reference's layer), summed over launches */
+  double bytes;      /* algorithmic HBM bytes (each operand once), summed over launches */
+} dc_profile_row;
+int dc_profile_enable(int on);
+int dc_profile_collect(dc_profile_row* rows, int cap, int* n);
+
 /* number of kernels this library has launched on the calling thread since load (bench.py's gpu_launches) */
 uint64_t dc_launch_count(void);
 
