@@ -262,6 +262,22 @@ def main():
     # ---------------------------------------------------------------- per-kernel roofline (rank 0's records)
     peaks = load_peaks()
     step_ms = sum(r["ms"] for r in rows) or 1.0
+    layer_rows = rows
+    by_class = {}
+    for r in rows:
+        c = by_class.setdefault(r["name"].split("[")[0], {"name": r["name"].split("[")[0], "launches": 0, "ms": 0.0,
+                                                          "flops": 0.0, "bytes": 0.0})
+        for f in ("launches", "ms", "flops", "bytes"):
+            c[f] += r[f]
+    rows = list(by_class.values())
+    layers = []
+    for r in sorted(layer_rows, key=lambda r: -r["ms"])[:40]:
+        e = {"name": r["name"], "launches_per_step": r["launches"] / K, "ms_per_step": round(r["ms"] / K, 3)}
+        if r["flops"] > 0 and r["ms"] > 0:
+            e["tflops"] = round(r["flops"] / (r["ms"] * 1e-3) / 1e12, 1)
+        if r["bytes"] > 0 and r["ms"] > 0:
+            e["gbs"] = round(r["bytes"] / (r["ms"] * 1e-3) / 1e9, 1)
+        layers.append(e)
     kernels = []
     for r in sorted(rows, key=lambda r: -r["ms"]):
         k = {"name": r["name"], "launches_per_step": r["launches"] / K, "ms_per_step": r["ms"] / K,
@@ -293,7 +309,7 @@ def main():
             "dtype": args.mode, "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": total_launches, "clocks": clocks, "roofline": roofline, "roofline_vq_score": vq,
-            "kernels": kernels,
+            "kernels": kernels, "layers": layers,
             "model_tflops": audio_s_per_step * (SR / HOP) * MFLOP_PER_FRAME * 1e6 * K / (ms_total / 1e3) / 1e12,
             "codes_checksum": checksum}
 

@@ -27,7 +27,7 @@ class DcConfig(C.Structure):
 
 class DcProfileRow(C.Structure):
     """dc_profile_row: per-kernel-class device time and algorithmic work."""
-    _fields_ = [("name", C.c_char * 32), ("launches", C.c_uint64), ("ms", C.c_double), ("flops", C.c_double),
+    _fields_ = [("name", C.c_char * 64), ("launches", C.c_uint64), ("ms", C.c_double), ("flops", C.c_double),
                 ("bytes", C.c_double)]
 
 

@@ -44,6 +44,7 @@ struct ProfRec {
   int cls;
   cudaEvent_t e0, e1;
   double flops, bytes;
+  char shape[40];
 };
 static thread_local bool g_prof_on = false;
 static thread_local std::vector<ProfRec> g_prof_recs;
@@ -59,10 +60,17 @@ static cudaEvent_t prof_event() {
   cudaEventCreate(&e);
   return e;
 }
-ProfScope::ProfScope(int cls, double flops, double bytes, cudaStream_t stream) : st(stream) {
+ProfScope::ProfScope(int cls, double flops, double bytes, cudaStream_t stream, const char* shape_fmt, ...)
+    : st(stream) {
   if (!g_prof_on) return;
-  ProfRec r{cls, prof_event(), prof_event(), flops, bytes};
+  ProfRec r{cls, prof_event(), prof_event(), flops, bytes, {0}};
   if (!r.e0 || !r.e1) return;
+  if (shape_fmt) {
+    va_list ap;
+    va_start(ap, shape_fmt);
+    vsnprintf(r.shape, sizeof(r.shape), shape_fmt, ap);
+    va_end(ap);
+  }
   cudaEventRecord(r.e0, st);
   idx = (int)g_prof_recs.size();
   g_prof_recs.push_back(r);
@@ -1058,8 +1066,8 @@ int dc_profile_enable(int on) {
 
 int dc_profile_collect(dc_profile_row* rows, int cap, int* n) {
   DC_CHECK(rows != nullptr && n != nullptr && cap >= 0, DC_ERR_ARG, "bad argument to dc_profile_collect");
-  dc_profile_row agg[PC_COUNT];
-  memset(agg, 0, sizeof(agg));
+  std::map<std::string, dc_profile_row> agg;
+  std::vector<std::string> order;
   int rc = DC_OK;
   for (ProfRec& r : g_prof_recs) {
     float ms = 0.f;
@@ -1067,21 +1075,27 @@ int dc_profile_collect(dc_profile_row* rows, int cap, int* n) {
       set_error("dc_profile_collect: event timing failed: %s", cudaGetErrorString(cudaGetLastError()));
       rc = DC_ERR_CUDA;
     }
-    agg[r.cls].launches += 1;
-    agg[r.cls].ms += ms;
-    agg[r.cls].flops += r.flops;
-    agg[r.cls].bytes += r.bytes;
+    std::string key = kProfNames[r.cls];
+    if (r.shape[0]) key += std::string("[") + r.shape + "]";
+    auto it = agg.find(key);
+    if (it == agg.end()) {
+      dc_profile_row row;
+      memset(&row, 0, sizeof(row));
+      strncpy(row.name, key.c_str(), sizeof(row.name) - 1);
+      it = agg.emplace(key, row).first;
+      order.push_back(key);
+    }
+    it->second.launches += 1;
+    it->second.ms += ms;
+    it->second.flops += r.flops;
+    it->second.bytes += r.bytes;
     g_prof_pool.push_back(r.e0);
     g_prof_pool.push_back(r.e1);
   }
   g_prof_recs.clear();
   int k = 0;
-  for (int c = 0; c < PC_COUNT; ++c) {
-    if (!agg[c].launches) continue;
-    if (k < cap) {
-      rows[k] = agg[c];
-      strncpy(rows[k].name, kProfNames[c], sizeof(rows[k].name) - 1);
-    }
+  for (const std::string& key : order) {
+    if (k < cap) rows[k] = agg[key];
     ++k;
   }
   *n = k;

@@ -143,7 +143,7 @@ enum ProfClass {
 struct ProfScope {
   int idx = -1;
   cudaStream_t st;
-  ProfScope(int cls, double flops, double bytes, cudaStream_t stream);
+  ProfScope(int cls, double flops, double bytes, cudaStream_t stream, const char* shape_fmt = nullptr, ...);
   ~ProfScope();
 };
 

@@ -279,11 +279,12 @@ class Engine:
 
     def profile_rows(self):
         """-> [{name, launches, ms, flops, bytes}] per kernel class since `profile(True)`; clears the records."""
-        rows = (_abi.DcProfileRow * 32)()
+        cap = 512
+        rows = (_abi.DcProfileRow * cap)()
         n = C.c_int()
-        _abi.check(self.lib.dc_profile_collect(rows, 32, C.byref(n)), "dc_profile_collect")
+        _abi.check(self.lib.dc_profile_collect(rows, cap, C.byref(n)), "dc_profile_collect")
         return [{"name": rows[i].name.decode(), "launches": int(rows[i].launches), "ms": rows[i].ms,
-                 "flops": rows[i].flops, "bytes": rows[i].bytes} for i in range(min(n.value, 32))]
+                 "flops": rows[i].flops, "bytes": rows[i].bytes} for i in range(min(n.value, cap))]
 
     def launch_count(self) -> int:
         return int(self.lib.dc_launch_count())

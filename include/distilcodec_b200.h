@@ -149,10 +149,10 @@ int dc_op_dwconv_ln(dc_handle h, const float* in_dev, const float* dw_w_dev, con
 
 /* Per-kernel-class device timing for roofline reports (thread-local, off by default).  While enabled, every kernel
  * launch is bracketed by a CUDA event pair on its stream and booked with its ALGORITHMIC flops and HBM bytes.
- * dc_profile_collect synchronises the recorded events, returns one row per kernel class that launched and clears
- * the records. */
+ * dc_profile_collect synchronises the recorded events, returns one row per kernel class and layer shape that
+ * launched (the part of `name` before '[' is the class) and clears the records. */
 typedef struct {
-  char name[32];     /* kernel class, e.g. "gemm_tc", "vq_score", "dwconv_ln" */
+  char name[64];     /* kernel class [+ shape], e.g. "gemm_tc[C256 N256 J3 d1 e5]", "vq_score", "dwconv_ln[C768]" */
   uint64_t launches;
   double ms;         /* sum of event-pair durations */
   double flops;      /* algorithmic FLOPs (2 x MACs of the reference's layer), summed over launches */
