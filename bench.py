@@ -124,7 +124,7 @@ def cpu_reference_rate(seconds_of_audio: float, clips: int, steps: int, warmup: 
     return audio_s / dt, dt / steps * 1e3, cores, T
 
 
-def run_reference_arm(args, rank: int, world: int):
+def run_reference_arm(args, rank: int, world: int, out):
     if rank != 0:
         return
     clips, secs = 1, 10.0
@@ -136,7 +136,7 @@ def run_reference_arm(args, rank: int, world: int):
             "config": workload_config(args, world),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 def workload_config(args, world: int) -> dict:
@@ -149,7 +149,17 @@ def workload_config(args, world: int) -> dict:
                   "input batches"}
 
 
+def _claim_stdout():
+    """Route everything that libraries print on fd 1 (e.g. NCCL's version banner) to stderr and return a file object
+    on the real stdout, so that the JSON line is the only thing printed there."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -168,7 +178,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank, world, out)
         return
 
     if not torch.cuda.is_available():
@@ -271,7 +281,7 @@ def main():
             c[f] += r[f]
     rows = list(by_class.values())
     layers = []
-    for r in sorted(layer_rows, key=lambda r: -r["ms"])[:40]:
+    for r in sorted(layer_rows, key=lambda r: -r["ms"])[:120]:
         e = {"name": r["name"], "launches_per_step": r["launches"] / K, "ms_per_step": round(r["ms"] / K, 3)}
         if r["flops"] > 0 and r["ms"] > 0:
             e["tflops"] = round(r["flops"] / (r["ms"] * 1e-3) / 1e12, 1)
@@ -322,7 +332,7 @@ def main():
     else:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

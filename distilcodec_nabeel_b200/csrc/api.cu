@@ -39,7 +39,7 @@ int sm_count_of_current_device() {
 // ---------------------------------------------------------------------------------------------- profiler
 static const char* kProfNames[PC_COUNT] = {"gemm_tc", "gemm_f32", "vq_score", "vq_prep", "vq_rescore",
                                            "vq_exhaustive", "dwconv_ln", "layernorm", "cast", "gather",
-                                           "transpose", "conv_post_tanh", "prepack"};
+                                           "transpose", "conv_post_tanh", "prepack", "conv_ws"};
 struct ProfRec {
   int cls;
   cudaEvent_t e0, e1;
@@ -1103,7 +1103,8 @@ int dc_profile_collect(dc_profile_row* rows, int cap, int* n) {
 }
 
 uint64_t dc_launch_count(void) {
-  return g_launches_api + gemm_tc_launch_count() + gemm_f32_launch_count() + pointwise_launch_count() + vq_launch_count();
+  return g_launches_api + gemm_tc_launch_count() + gemm_f32_launch_count() + pointwise_launch_count() +
+         vq_launch_count() + conv_ws_launch_count();
 }
 
 }  // extern "C"

@@ -96,6 +96,11 @@ int launch_gemm_f32(const float* A, const float* W, const ConvGemmShape& s, cons
 int launch_gemm_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
                    cudaStream_t st, int sm_count);
 size_t gemm_tc_launch_count();
+// weights-stationary, tap-shared variant for C in {32, 64}, N <= 64 (conv_ws.cu); same operands as launch_gemm_tc
+bool conv_ws_supported(const ConvGemmShape& s);
+int launch_conv_ws(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
+                   cudaStream_t st, int sm_count);
+uint64_t conv_ws_launch_count();
 
 // pointwise / bandwidth-bound kernels (pointwise.cu)
 int launch_transpose_ncl_to_nlc(const float* in, void* out, int out_dt, int B, int C, int T, cudaStream_t st);
@@ -138,7 +143,7 @@ int sm_count_of_current_device();
 // CUDA event pair on the launching stream and books the launch's ALGORITHMIC flops / HBM bytes.
 enum ProfClass {
   PC_GEMM_TC = 0, PC_GEMM_F32, PC_VQ_SCORE, PC_VQ_PREP, PC_VQ_RESCORE, PC_VQ_EXHAUSTIVE, PC_DWCONV_LN, PC_LAYERNORM,
-  PC_CAST, PC_GATHER, PC_TRANSPOSE, PC_CONV_POST, PC_PREPACK, PC_COUNT
+  PC_CAST, PC_GATHER, PC_TRANSPOSE, PC_CONV_POST, PC_PREPACK, PC_CONV_WS, PC_COUNT
 };
 struct ProfScope {
   int idx = -1;

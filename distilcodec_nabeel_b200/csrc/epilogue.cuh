@@ -1,0 +1,238 @@
+// Fused epilogue of the tcgen05 implicit-GEMM kernels (gemm_tc.cu, conv_ws.cu): bias / activation / LayerScale /
+// residual / 3-branch mean / dual fp32 + bf16(SiLU) stores, applied to 128 x BN accumulator tiles read from TMEM.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dc {
+
+// ---------------------------------------------------------------- epilogue helpers (4 consecutive columns per lane)
+// After the per-warp shared-memory transpose a lane owns 4 consecutive output columns of one row, so that a
+// quarter-warp covers 128 contiguous bytes of an fp32 row (64 of a bf16 row) and every global access is a full
+// sector: the residual / mean operands are read and both outputs written fully coalesced.
+__device__ __forceinline__ float silu_fast(float x) {  // x * sigmoid(x): 2 MUFU + 3 FP32 ops, ~1e-6 relative
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return x * r;
+}
+// exact-erf GELU (nn.GELU(), convnext_utils.py:254) with erf from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far
+// below the bf16 rounding of the stored result): 2 MUFU + 10 FP32 ops instead of erff's ~25 with branches
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erf_abs = fmaf(-p * t, e, 1.f);          // erf(|x| / sqrt 2)
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float4 ld4(const void* base, size_t off, int dt) {
+  if (dt == DT_F32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+  const uint2 x = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+  return make_float4(__uint_as_float(x.x << 16), __uint_as_float(x.x & 0xffff0000u), __uint_as_float(x.y << 16),
+                     __uint_as_float(x.y & 0xffff0000u));
+}
+__device__ __forceinline__ void st4(void* base, size_t off, int dt, const float4 v) {
+  if (dt == DT_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = v;
+  } else {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = pk;
+  }
+}
+__device__ __forceinline__ float4 ld4_nc(const void* base, size_t off, int dt) {  // read-only for the whole launch
+  if (dt == DT_F32) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off));
+  const uint2 x = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + off));
+  return make_float4(__uint_as_float(x.x << 16), __uint_as_float(x.x & 0xffff0000u), __uint_as_float(x.y << 16),
+                     __uint_as_float(x.y & 0xffff0000u));
+}
+// v: accumulators of columns n..n+3 of output row `row`; bias/gamma already loaded for these columns; r = the
+// residual values (pre-loaded by the caller for the whole chunk: `res` may alias `out0`, so the compiler cannot
+// move those loads above earlier stores by itself and the 8 row groups would serialise on memory latency)
+__device__ __forceinline__ void epilogue4(const Epilogue& e, size_t row, int n, float4 v, const float4 b,
+                                          const float4 g, const float4 r) {
+  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  if (e.act == ACT_GELU) {
+    v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w);
+  } else if (e.act == ACT_SILU) {
+    v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w);
+  }
+  v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+  const size_t off = row * (size_t)e.ldo + n;
+  v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+  if (e.add1) {  // the other two branch results: never written by this launch
+    const float4 a = ld4_nc(e.add1, off, e.add_dt), c = ld4_nc(e.add2, off, e.add_dt);
+    v.x = (v.x + a.x + c.x) * e.scale; v.y = (v.y + a.y + c.y) * e.scale;
+    v.z = (v.z + a.z + c.z) * e.scale; v.w = (v.w + a.w + c.w) * e.scale;
+  }
+  if (e.out0) st4(e.out0, off, e.out0_dt, v);
+  if (e.out1) {
+    if (e.out1_silu) {
+      v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w);
+    }
+    st4(e.out1, off, e.out1_dt, v);
+  }
+}
+
+// ---------------------------------------------------------------- specialised epilogues
+// The runtime-flag epilogue above costs ~30 instructions per element (flag tests, 64-bit address arithmetic, dtype
+// dispatch) and the 8 epilogue warps cannot hide that; the variants below are the epilogues the hot path actually
+// uses, with every flag a compile-time constant.  The host picks the variant (epilogue_variant()).
+enum { EV_GENERIC = 0, EV_SILU_BF16, EV_RES_F32_BF16S, EV_RES_F32, EV_RES_MEAN_BF16S, EV_F32_BF16S, EV_GELU_BF16,
+       EV_GAMMA_RES_F32, EV_F32, EV_BF16 };
+
+static inline int epilogue_variant(const Epilogue& e) {
+  const bool res32 = e.res && e.res_dt == DT_F32, o0f = e.out0 && e.out0_dt == DT_F32,
+             o0b = e.out0 && e.out0_dt == DT_BF16, o1s = e.out1 && e.out1_dt == DT_BF16 && e.out1_silu;
+  if (e.out1 && !o1s) return EV_GENERIC;
+  if (e.res && !res32) return EV_GENERIC;
+  if (e.add1) return (e.add_dt == DT_F32 && !e.act && !e.gamma && res32 && !e.out0 && o1s) ? EV_RES_MEAN_BF16S : EV_GENERIC;
+  if (e.gamma) return (!e.act && res32 && o0f && !e.out1) ? EV_GAMMA_RES_F32 : EV_GENERIC;
+  if (e.act == ACT_SILU) return (!e.res && o0b && !e.out1) ? EV_SILU_BF16 : EV_GENERIC;
+  if (e.act == ACT_GELU) return (!e.res && o0b && !e.out1) ? EV_GELU_BF16 : EV_GENERIC;
+  if (res32) return o0f ? (o1s ? EV_RES_F32_BF16S : (e.out1 ? EV_GENERIC : EV_RES_F32)) : EV_GENERIC;
+  if (o0f) return o1s ? EV_F32_BF16S : (e.out1 ? EV_GENERIC : EV_F32);
+  if (o0b && !e.out1) return EV_BF16;
+  return EV_GENERIC;
+}
+
+__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, const float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
+// One 32-row x CW-column chunk of one warp.  stg: the warp's XOR-swizzled transpose tile (already written);
+// off0: element offset (row * ldo + n) of this lane's first row group; nvalid: row groups of this lane with t < T.
+template <int V, int CW>
+__device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, const float* stg, int lane, size_t off0,
+                                               int nvalid, const float4 b4, const float4 g4) {
+  constexpr int CPR = CW / 4, RPI = 32 / CPR, NG = 32 / RPI;
+  constexpr bool kRes = V == EV_RES_F32_BF16S || V == EV_RES_F32 || V == EV_RES_MEAN_BF16S || V == EV_GAMMA_RES_F32;
+  constexpr bool kOut0F = V == EV_RES_F32_BF16S || V == EV_RES_F32 || V == EV_F32_BF16S || V == EV_GAMMA_RES_F32 || V == EV_F32;
+  constexpr bool kOut0B = V == EV_SILU_BF16 || V == EV_GELU_BF16 || V == EV_BF16;
+  constexpr bool kOut1 = V == EV_RES_F32_BF16S || V == EV_RES_MEAN_BF16S || V == EV_F32_BF16S;
+  const int cg = lane % CPR, rsub = lane / CPR;
+  const size_t stride = (size_t)RPI * ep.ldo;
+  float4 r4[NG];
+  if constexpr (kRes) {
+    const float* rp = reinterpret_cast<const float*>(ep.res) + off0;
+#pragma unroll
+    for (int k = 0; k < NG; ++k)
+      r4[k] = k < nvalid ? *reinterpret_cast<const float4*>(rp + k * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < NG; ++k) {
+    const int r = k * RPI + rsub;
+    const int rswz = CW == 32 ? (r & 7) : ((r >> 1) & 3);
+    float4 v = *reinterpret_cast<const float4*>(stg + r * CW + ((cg ^ rswz) << 2));
+    if (k < nvalid) {
+      const size_t off = off0 + k * stride;
+      v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+      if constexpr (V == EV_SILU_BF16) {
+        v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w);
+      }
+      if constexpr (V == EV_GELU_BF16) {
+        v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w);
+      }
+      if constexpr (V == EV_GAMMA_RES_F32) {
+        v.x *= g4.x; v.y *= g4.y; v.z *= g4.z; v.w *= g4.w;
+      }
+      if constexpr (kRes) {
+        v.x += r4[k].x; v.y += r4[k].y; v.z += r4[k].z; v.w += r4[k].w;
+      }
+      if constexpr (V == EV_RES_MEAN_BF16S) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.add1) + off));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.add2) + off));
+        v.x = (v.x + a.x + c.x) * ep.scale; v.y = (v.y + a.y + c.y) * ep.scale;
+        v.z = (v.z + a.z + c.z) * ep.scale; v.w = (v.w + a.w + c.w) * ep.scale;
+      }
+      if constexpr (kOut0F) *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out0) + off) = v;
+      if constexpr (kOut0B) st_bf16x4(reinterpret_cast<__nv_bfloat16*>(ep.out0) + off, v);
+      if constexpr (kOut1) {
+        v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w);
+        st_bf16x4(reinterpret_cast<__nv_bfloat16*>(ep.out1) + off, v);
+      }
+    }
+  }
+}
+
+// generic (runtime-flag) chunk
+template <int CW>
+__device__ __forceinline__ void epilogue_chunk_generic(const Epilogue& ep, const float* stg, int lane, size_t off0,
+                                                       int nvalid, int n, const float4 b4, const float4 g4) {
+  constexpr int CPR = CW / 4, RPI = 32 / CPR, NG = 32 / RPI;
+  const int cg = lane % CPR, rsub = lane / CPR;
+  const size_t stride = (size_t)RPI * ep.ldo;
+  float4 r4[NG];
+#pragma unroll
+  for (int k = 0; k < NG; ++k)
+    r4[k] = (ep.res && k < nvalid) ? ld4(ep.res, off0 + k * stride, ep.res_dt) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < NG; ++k) {
+    const int r = k * RPI + rsub;
+    const int rswz = CW == 32 ? (r & 7) : ((r >> 1) & 3);
+    const float4 v = *reinterpret_cast<const float4*>(stg + r * CW + ((cg ^ rswz) << 2));
+    if (k < nvalid) epilogue4(ep, (off0 + k * stride - n) / ep.ldo, n, v, b4, g4, r4[k]);
+  }
+}
+
+// One 128 x BN output tile: the 8 epilogue warps (CTA warps 2..9) each take a TMEM lane quarter (rows) and one half of
+// the columns.  TMEM -> registers (thread = row) -> XOR-swizzled per-warp smem tile -> (lane = 4 columns) -> global.
+// tmem_acc: TMEM address (lane 0) of the tile's accumulator; stg: this warp's 32 x CW fp32 transpose buffer.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int variant, float* stg, uint32_t tmem_acc, int clip,
+                                              int t0, int n0, int T, int warp, int lane) {
+  constexpr int CW = BN >= 64 ? 32 : 16;  // chunk width in columns
+  constexpr int CPR = CW / 4;             // 16-byte column groups per row (8 or 4)
+  constexpr int RPI = 32 / CPR;           // rows covered by one warp-wide access (4 or 8)
+  const int q = warp & 3;                 // TMEM lane quarter this warp may access
+  const int half = (warp - 2) >> 2;       // which half of the tile's columns it takes
+  const int cg = lane % CPR, rsub = lane / CPR;
+#pragma unroll 1
+  for (int c = 0; c < (BN / 2) / CW; ++c) {
+    const int col0 = half * (BN / 2) + c * CW;  // first column of this chunk within the tile
+    uint32_t acc[CW];
+    if constexpr (CW == 32) ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, acc);
+    else ptx::tmem_ld_32x16(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, acc);
+    // column parameters of this lane's 4 columns (independent of the row)
+    const int n = n0 + col0 + cg * 4;
+    const float4 b4 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 g4 = ep.gamma ? __ldg(reinterpret_cast<const float4*>(ep.gamma + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    ptx::tmem_ld_wait();
+    // thread = row `lane`: 16-byte group i goes to slot (i ^ swz(lane)); conflict-free for both access phases
+    const int wswz = CW == 32 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+    for (int i = 0; i < CPR; ++i)
+      *reinterpret_cast<uint4*>(stg + lane * CW + ((i ^ wswz) << 2)) =
+          make_uint4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    __syncwarp();
+    const int tb = t0 + q * 32 + rsub;  // first row of this lane
+    const int nvalid = min(32 / RPI, max(0, (T - tb + RPI - 1) / RPI));
+    const size_t off0 = ((size_t)clip * T + tb) * (size_t)ep.ldo + n;
+    switch (variant) {
+      case EV_SILU_BF16: epilogue_chunk<EV_SILU_BF16, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
+      case EV_RES_F32_BF16S: epilogue_chunk<EV_RES_F32_BF16S, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
+      case EV_RES_F32: epilogue_chunk<EV_RES_F32, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
+      case EV_RES_MEAN_BF16S: epilogue_chunk<EV_RES_MEAN_BF16S, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
+      case EV_F32_BF16S: epilogue_chunk<EV_F32_BF16S, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
+      case EV_GELU_BF16: epilogue_chunk<EV_GELU_BF16, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
+      case EV_GAMMA_RES_F32: epilogue_chunk<EV_GAMMA_RES_F32, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
+      case EV_F32: epilogue_chunk<EV_F32, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
+      case EV_BF16: epilogue_chunk<EV_BF16, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
+      default: epilogue_chunk_generic<CW>(ep, stg, lane, off0, nvalid, n, b4, g4); break;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace dc
