@@ -165,7 +165,8 @@ struct dc_handle_s {
   int K = 0, CD = 0;
   // generator
   Dense conv_pre, ups[8], rb[8][3][2][3];
-  float* post_w = nullptr;  // [k][C_last]
+  float* post_w = nullptr;  // [k][C_last] (device copy)
+  float post_w_host[13 * 32] = {};  // passed to the kernel as a parameter (constant bank)
   float post_b = 0.f;
   int post_C = 0;
 };
@@ -563,7 +564,7 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
   }
   ar.release(m0);
   if (!dry)  // silu (folded above) -> conv_post -> tanh (generators.py:141-145)
-    DC_TRY(launch_conv_post_tanh(carry[cur], ad, h->post_w, h->post_b, wav, B, L, st));
+    DC_TRY(launch_conv_post_tanh(carry[cur], ad, h->post_w_host, h->post_b, wav, B, L, st));
   return DC_OK;
 }
 
@@ -836,7 +837,8 @@ int dc_finalize(dc_handle h, void* stream) {
         rc = launch_pack_weight(scratch, pd, h->post_w, nullptr, st);
         if (rc) break;
         h->post_C = Cl;
-        if (cudaMemcpyAsync(&h->post_b, b->d, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+        if (cudaMemcpyAsync(h->post_w_host, h->post_w, sizeof(h->post_w_host), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(&h->post_b, b->d, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
           set_error("conv_post bias copy failed");
           rc = DC_ERR_CUDA;
         }

@@ -111,8 +111,8 @@ int launch_dwconv_ln(const float* in, const float* dw_w /*[7][C]*/, const float*
 int launch_cast(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st);
 int launch_gather_rows(const float* table, const int64_t* idx, int64_t nrows, int D, int64_t table_rows,
                        float* out_f32 /*nullable*/, __nv_bfloat16* out_bf16 /*nullable*/, cudaStream_t st);
-int launch_conv_post_tanh(const void* in, int in_dt, const float* w /*[13][32]*/, float bias, float* out, int B,
-                          int L, cudaStream_t st);
+int launch_conv_post_tanh(const void* in, int in_dt, const float* w_host /*[13][32], HOST memory*/, float bias,
+                          float* out, int B, int L, cudaStream_t st);
 // weight prepack helpers
 int launch_weight_norm_fold(const float* g, const float* v, float* w, int dim0, int inner, cudaStream_t st);
 struct PackDesc {

@@ -2,6 +2,8 @@
 // weight prepack kernels.  All activations are channels-last (rows = frames, C contiguous).
 #include "common.cuh"
 
+#include <string.h>
+
 namespace dc {
 
 static thread_local uint64_t g_launches_pw = 0;
@@ -127,6 +129,138 @@ __global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict_
   }
 }
 
+// ---- depthwise k7 + LayerNorm, sliding-window form (the ConvNeXt blocks' kernel) ------------------------------------
+// A block owns RUN consecutive frames of one clip and all C channels; thread i owns channels 4i..4i+3 for the whole
+// run, so its 7 x 4 depthwise weights, bias and LayerNorm affine live in registers and every input row is loaded from
+// global memory exactly ONCE (7-row register window; the warp-per-frame kernel above re-reads each row 7 times
+// through L1, which caps it at ~0.4 of HBM peak).  Rows are processed in batches of R so that R row loads are in
+// flight per thread; LayerNorm statistics are two-pass (mean, then centred sum of squares) across the block's warps
+// through shared memory.  Algorithmic HBM bytes per frame: C*4 read + C*sizeof(TOut) written.
+template <int C, typename TOut>
+__global__ void __launch_bounds__(C / 4) dwconv_ln_run_kernel(const float* __restrict__ in,
+                                                              const float* __restrict__ dw_w /*[7][C]*/,
+                                                              const float* __restrict__ dw_b,
+                                                              const float* __restrict__ ln_w,
+                                                              const float* __restrict__ ln_b, TOut* __restrict__ out,
+                                                              int T, int run) {
+  constexpr int NW = C / 128, R = 8;
+  // prefetching costs 32 registers: at C = 1024 (256 threads) that halves the resident blocks and loses more than
+  // it gains (measured 2.7 vs 3.4 TB/s); below that it wins (C = 768: 3.7 vs 3.1 TB/s)
+  constexpr bool PREFETCH = C <= 768;
+  __shared__ float red[2][R][NW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = tid * 4;
+  const int t_begin = blockIdx.x * run, t_end = min(T, t_begin + run);
+  const float* ib = in + (size_t)blockIdx.y * T * C + c;
+  TOut* ob = out + (size_t)blockIdx.y * T * C + c;
+  float4 w[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) w[j] = __ldg(reinterpret_cast<const float4*>(dw_w + (size_t)j * C + c));
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(dw_b + c));
+  const float4 gw = __ldg(reinterpret_cast<const float4*>(ln_w + c));
+  const float4 gb = __ldg(reinterpret_cast<const float4*>(ln_b + c));
+  auto load_row = [&](int t) -> float4 {
+    return (t >= 0 && t < T) ? __ldg(reinterpret_cast<const float4*>(ib + (size_t)t * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 x[7 + R - 1];  // window: x[k] = row t0 - 3 + k
+  float4 nx[R];         // the R new rows of the NEXT batch, prefetched while this batch is reduced and stored
+#pragma unroll
+  for (int k = 0; k < 6; ++k) x[k] = load_row(t_begin - 3 + k);
+  if constexpr (PREFETCH) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) nx[r] = load_row(t_begin + 3 + r);
+  }
+  for (int t0 = t_begin; t0 < t_end; t0 += R) {
+    if constexpr (PREFETCH) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) x[6 + r] = nx[r];
+      if (t0 + R < t_end) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) nx[r] = load_row(t0 + R + 3 + r);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) x[6 + r] = load_row(t0 + 3 + r);
+    }
+    float4 y[R];
+    float s[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float4 a = bias;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        a.x = fmaf(x[r + j].x, w[j].x, a.x); a.y = fmaf(x[r + j].y, w[j].y, a.y);
+        a.z = fmaf(x[r + j].z, w[j].z, a.z); a.w = fmaf(x[r + j].w, w[j].w, a.w);
+      }
+      y[r] = a;
+      s[r] = warp_sum((a.x + a.y) + (a.z + a.w));
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) red[0][r][warp] = s[r];
+    }
+    __syncthreads();
+    float mean[R], q[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float m = 0.f;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) m += red[0][r][k];
+      mean[r] = m * (1.f / C);
+      const float dx = y[r].x - mean[r], dy = y[r].y - mean[r], dz = y[r].z - mean[r], dw = y[r].w - mean[r];
+      q[r] = warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw));
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) red[1][r][warp] = q[r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) v += red[1][r][k];
+      const float rstd = rsqrtf(v * (1.f / C) + 1e-6f);
+      const int t = t0 + r;
+      if (t < t_end) {
+        float4 o;
+        o.x = (y[r].x - mean[r]) * rstd * gw.x + gb.x;
+        o.y = (y[r].y - mean[r]) * rstd * gw.y + gb.y;
+        o.z = (y[r].z - mean[r]) * rstd * gw.z + gb.z;
+        o.w = (y[r].w - mean[r]) * rstd * gw.w + gb.w;
+        if constexpr (sizeof(TOut) == 4) {
+          *reinterpret_cast<float4*>(ob + (size_t)t * C) = o;
+        } else {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(ob + (size_t)t * C) = pk;
+        }
+      }
+    }
+    // slide the window by R rows; the next batch's writes to red[0] are ordered after this batch's reads of red[0]
+    // by the second __syncthreads above, and its writes to red[1] after these reads by its own first __syncthreads
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x[k] = x[k + R];
+  }
+}
+
+template <int C>
+static int dwconv_ln_run_dispatch(const float* in, const float* dw_w, const float* dw_b, const float* ln_w,
+                                  const float* ln_b, void* out, int out_dt, int B, int T, cudaStream_t st) {
+  const int run = 64;
+  dim3 grid((T + run - 1) / run, B);
+  ProfScope ps(PC_DWCONV_LN, 0, (double)B * T * C * (4.0 + (out_dt == DT_F32 ? 4.0 : 2.0)), st, "C%d", C);
+  if (out_dt == DT_F32)
+    dwconv_ln_run_kernel<C, float><<<grid, C / 4, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (float*)out, T, run);
+  else
+    dwconv_ln_run_kernel<C, __nv_bfloat16><<<grid, C / 4, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (__nv_bfloat16*)out, T, run);
+  ++g_launches_pw;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
 template <int VPL>
 static int dwconv_ln_dispatch(const float* in, const float* dw_w, const float* dw_b, const float* ln_w,
                               const float* ln_b, void* out, int out_dt, int B, int T, cudaStream_t st) {
@@ -149,6 +283,15 @@ static int dwconv_ln_dispatch(const float* in, const float* dw_w, const float* d
 
 int launch_dwconv_ln(const float* in, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b,
                      void* out, int out_dt, int B, int T, int C, cudaStream_t st) {
+  if (dw_w) {  // depthwise conv + LN: sliding-window kernel
+    switch (C) {
+      case 256: return dwconv_ln_run_dispatch<256>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
+      case 512: return dwconv_ln_run_dispatch<512>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
+      case 768: return dwconv_ln_run_dispatch<768>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
+      case 1024: return dwconv_ln_run_dispatch<1024>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
+      default: set_error("dwconv_ln: unsupported channel count %d (256/512/768/1024)", C); return DC_ERR_SHAPE;
+    }
+  }
   switch (C) {
     case 256: return dwconv_ln_dispatch<2>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
     case 512: return dwconv_ln_dispatch<4>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
@@ -221,41 +364,91 @@ int launch_gather_rows(const float* table, const int64_t* idx, int64_t nrows, in
 
 // ------------------------------------------------------------------------------------------ conv_post + tanh
 // Conv1d(32 -> 1, k13, pad 6) + tanh (models/generators.py:141-145) on the already SiLU'd channels-last input.
-// 256 outputs per block; the (256+12) x 32 input slab is staged in padded shared memory (row pitch 33 words).
+// 416 FMAs per output sample and a single output channel: CUDA-core work.  Each thread produces 4 consecutive
+// samples, so per input channel it needs 16 consecutive rows (four conflict-free LDS.128 from a channel-major
+// shared-memory tile) for 52 FMAs whose weight operand comes straight from the kernel-parameter constant bank.
+struct ConvPostW {
+  float w[13 * 32];  // [tap][channel]
+};
 template <typename TIn>
-__global__ void __launch_bounds__(256) conv_post_tanh_kernel(const TIn* __restrict__ in, const float* __restrict__ w,
-                                                             float bias, float* __restrict__ out, int L) {
-  constexpr int C = 32, K = 13, TILE = 256;
-  __shared__ float sx[(TILE + K - 1) * 33];
-  __shared__ float sw[K * C];
+__global__ void __launch_bounds__(128) conv_post_tanh_kernel(const TIn* __restrict__ in, const ConvPostW W, float bias,
+                                                             float* __restrict__ out, int L) {
+  constexpr int C = 32, K = 13, TILE = 512, ROWS = TILE + 16;  // 12 halo rows + 4 padding (float4 alignment)
+  extern __shared__ float sx[];                                // [C][ROWS]
   const int b = blockIdx.y, l0 = blockIdx.x * TILE;
   const TIn* ib = in + (size_t)b * L * C;
-  for (int i = threadIdx.x; i < K * C; i += 256) sw[i] = w[i];
-  for (int i = threadIdx.x; i < (TILE + K - 1) * C; i += 256) {
-    const int r = i / C, c = i % C, l = l0 + r - 6;
-    float v = 0.f;
-    if (l >= 0 && l < L) {
-      if constexpr (sizeof(TIn) == 4) v = ib[(size_t)l * C + c];
-      else v = __bfloat162float(ib[(size_t)l * C + c]);
+  // fill: lane = row, 8 channels per 16-byte load (bf16) / 4 per load (fp32); transposed store is conflict-free
+  for (int r = threadIdx.x; r < ROWS; r += 128) {
+    const int l = l0 + r - 6;
+    const bool ok = l >= 0 && l < L;
+    if constexpr (sizeof(TIn) == 2) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) v = __ldg(reinterpret_cast<const uint4*>(ib + (size_t)l * C) + g);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          sx[(g * 8 + 2 * k) * ROWS + r] = __uint_as_float(u[k] << 16);
+          sx[(g * 8 + 2 * k + 1) * ROWS + r] = __uint_as_float(u[k] & 0xffff0000u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) v = __ldg(reinterpret_cast<const float4*>(ib + (size_t)l * C) + g);
+        sx[(g * 4 + 0) * ROWS + r] = v.x; sx[(g * 4 + 1) * ROWS + r] = v.y;
+        sx[(g * 4 + 2) * ROWS + r] = v.z; sx[(g * 4 + 3) * ROWS + r] = v.w;
+      }
     }
-    sx[r * 33 + c] = v;
   }
   __syncthreads();
-  const int l = l0 + threadIdx.x;
-  if (l >= L) return;
-  float acc = bias;
+  const int r0 = threadIdx.x * 4;  // this thread's outputs l0 + r0 .. + 3 need tile rows r0 .. r0 + 15
+  float acc[4] = {bias, bias, bias, bias};
 #pragma unroll
-  for (int j = 0; j < K; ++j)
+  for (int c = 0; c < C; ++c) {
+    float x[16];
+    const float4* p = reinterpret_cast<const float4*>(sx + c * ROWS + r0);
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc = fmaf(sx[(threadIdx.x + j) * 33 + c], sw[j * C + c], acc);
-  out[(size_t)b * L + l] = tanhf(acc);
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = p[i];
+      x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const float wj = W.w[j * C + c];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = fmaf(x[o + j], wj, acc[o]);
+    }
+  }
+  const int l = l0 + r0;
+  float* ob = out + (size_t)b * L;
+  if (l + 3 < L) {
+    *reinterpret_cast<float4*>(ob + l) = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
+  } else {
+    for (int o = 0; o < 4; ++o)
+      if (l + o < L) ob[l + o] = tanhf(acc[o]);
+  }
 }
-int launch_conv_post_tanh(const void* in, int in_dt, const float* w, float bias, float* out, int B, int L,
-                          cudaStream_t st) {
-  dim3 grid((L + 255) / 256, B);
+int launch_conv_post_tanh(const void* in, int in_dt, const float* w_host /*[13][32], host*/, float bias, float* out,
+                          int B, int L, cudaStream_t st) {
+  DC_CHECK(L % 4 == 0, DC_ERR_SHAPE, "conv_post: output length must be a multiple of 4");
+  ConvPostW W;
+  memcpy(W.w, w_host, sizeof(W.w));
+  constexpr int SMEM = 32 * (512 + 16) * 4;
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  DC_CUDA(cudaGetDevice(&dev));
+  if (!(attr_dev_mask & (1 << dev))) {
+    DC_CUDA(cudaFuncSetAttribute(conv_post_tanh_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    DC_CUDA(cudaFuncSetAttribute(conv_post_tanh_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_dev_mask |= 1 << dev;
+  }
+  dim3 grid((L + 511) / 512, B);
   ProfScope ps(PC_CONV_POST, 2.0 * B * (double)L * 32 * 13, (double)B * L * (32.0 * (in_dt == DT_F32 ? 4 : 2) + 4.0), st);
-  if (in_dt == DT_F32) conv_post_tanh_kernel<float><<<grid, 256, 0, st>>>((const float*)in, w, bias, out, L);
-  else conv_post_tanh_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, w, bias, out, L);
+  if (in_dt == DT_F32) conv_post_tanh_kernel<float><<<grid, 128, SMEM, st>>>((const float*)in, W, bias, out, L);
+  else conv_post_tanh_kernel<__nv_bfloat16><<<grid, 128, SMEM, st>>>((const __nv_bfloat16*)in, W, bias, out, L);
   ++g_launches_pw;
   DC_CUDA(cudaGetLastError());
   return DC_OK;

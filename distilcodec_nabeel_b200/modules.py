@@ -17,7 +17,7 @@ fp32 engine.  Engines are created lazily per mode from the same state_dict.
 from __future__ import annotations
 
 from collections import OrderedDict
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, Optional
 
 import torch
@@ -28,16 +28,18 @@ from .engine import Engine, load_config
 
 @dataclass
 class GRVQResult:
-    """Field-for-field mirror of vector_quantization/grfvq.py:13-24."""
+    """Field-for-field mirror of vector_quantization/grfvq.py:13-24 (same names, same order).  The three `*_list`
+    fields start empty; DistilCodec.encode appends the per-clip tokens / features to them (distil_codec.py:563-570)."""
     quantized: torch.Tensor
     codes: torch.Tensor
+    codes_list: list
     total_loss: torch.Tensor
     commitment_loss: torch.Tensor
     codebook_diversity_loss: torch.Tensor
     quantized_fup: torch.Tensor
+    quantized_fup_list: list
     x_pjt_in: torch.Tensor
-    commitment_loss_list: list = field(default_factory=list)
-    codebook_diversity_loss_list: list = field(default_factory=list)
+    x_pjt_in_list: list
 
 
 class EngineSet:
@@ -110,7 +112,7 @@ class _Shim(nn.Module):
 
     def _dev(self, x: torch.Tensor) -> torch.Tensor:
         eng_dev = self._engines.device
-        if eng_dev.index is None:
+        if eng_dev.type == "cuda" and eng_dev.index is None:
             eng_dev = torch.device("cuda", torch.cuda.current_device())
             self._engines.device = eng_dev
         if x.device != eng_dev:
@@ -157,8 +159,9 @@ class B200Quantizer(_Shim):
         codes, xin, fup, quant = eng.quantizer(z_nlc, want_fup=True)
         zero = torch.zeros((), dtype=torch.float32, device=z.device)  # eval-mode losses are 0 (vq :974,:1056)
         B, T = codes.shape
-        return GRVQResult(quantized=quant.transpose(1, 2), codes=codes.view(1, B, T, 1), total_loss=zero,
-                          commitment_loss=zero, codebook_diversity_loss=zero, quantized_fup=fup, x_pjt_in=xin)
+        return GRVQResult(quantized=quant.transpose(1, 2), codes=codes.view(1, B, T, 1), codes_list=[],
+                          total_loss=zero, commitment_loss=zero, codebook_diversity_loss=zero, quantized_fup=fup,
+                          quantized_fup_list=[], x_pjt_in=xin, x_pjt_in_list=[])
 
     @torch.no_grad()
     def encode(self, z: torch.Tensor) -> torch.Tensor:

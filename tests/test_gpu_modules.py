@@ -43,7 +43,7 @@ def test_forward_like_distilcodec_forward(codec):
     assert r.codes.shape == (1, 2, 40, 1) and r.codes.dtype == torch.int64
     assert r.quantized.shape == (2, 1024, 40) and r.quantized_fup.shape == (2, 40, 3584)
     assert r.x_pjt_in.shape == (2, 40, 3584)
-    assert float(r.total_loss) == 0.0 and r.commitment_loss_list == []
+    assert float(r.total_loss) == 0.0 and r.codes_list == [] and r.x_pjt_in_list == [] and r.quantized_fup_list == []
     wav = codec.generator(r.quantized)
     assert wav.shape == (2, 1, 10240)
     assert np.array_equal(r.codes.cpu().numpy(), g["codes"])
@@ -60,7 +60,7 @@ def test_autocast_selects_the_bf16_engine(codec):
         r = codec.quantizer(enc)
         wav = codec.generator(r.quantized)
     assert enc.dtype == torch.float32 and r.x_pjt_in.dtype == torch.bfloat16
-    assert rel_err(enc, torch.from_numpy(g["enc"])) < 1e-2
+    assert rel_err(enc, torch.from_numpy(g["enc"])) < 2e-2      # W1 stress weights: see tests/test_gpu_e2e.py
     assert wav.shape == (2, 1, 10240)
 
 
