@@ -288,7 +288,15 @@ int launch_gemm_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGem
     if (s.N % 64 == 0) return launch_cfg<64, 32, 8>(A, W, s, e, st, sm_count);
     return launch_cfg<32, 32, 8>(A, W, s, e, st, sm_count);
   }
-  if (s.N % 256 == 0) return launch_cfg<256, 64, 4>(A, W, s, e, st, sm_count);
+  if (s.N % 256 == 0) {
+    // residual / dual-output epilogues (the decoder's conv2) are an HBM latency chain of ~20k cycles per 128 x 256
+    // tile; when the tile's MMAs are shorter than that (K <= 1792: C = 256 with k = 3, 7) two epilogue groups, one
+    // per TMEM accumulator, pay for the operand stage they cost (measured: 6.7 -> 5.7 ms, 8.3 -> 7.6 ms; with
+    // longer K or two N tiles the shallower operand ring loses more than the epilogue gains)
+    if ((e.res || (e.out0 && e.out1)) && s.J * s.C <= 1792 && s.N == 256)
+      return launch_cfg<256, 64, 3, 2, 2>(A, W, s, e, st, sm_count);
+    return launch_cfg<256, 64, 4>(A, W, s, e, st, sm_count);
+  }
   if (s.N % 128 == 0) {
     // short-K layers (the C = 128 decoder stage, K <= 1408) are bound by the epilogue's HBM latency chain: two
     // epilogue groups on alternate tiles; long-K layers are tensor-bound and keep the deeper operand pipeline

@@ -646,9 +646,21 @@ int launch_vq_search(const void* x, int x_dt, const float* x2_opt, int64_t nrows
   if (use_tc && K % VQ_BN == 0) {
     const int n_mblk = (int)((nrows + VQ_BM - 1) / VQ_BM);
     const int n_tiles = K / VQ_BN;
-    // split the codebook so that (row blocks x splits) fills the persistent grid evenly
+    // Work item = (256-row block, codebook split); item i -> (block i / NS, split i % NS), so the sm_count items in
+    // flight cover sm_count / NS row blocks x NS splits.  Every CTA re-reads its 256 x D x-panel (1.8 MB at D = 3584)
+    // from L2 once per codebook tile, and the CTAs of one split stream the same codebook tiles in step, so the set
+    // of x-panels in flight must stay L2-resident: (sm_count / NS) * panel <= ~64 MB  ->  NS >= 4 on B200.
+    // (With NS = 2 the panels thrash: ncu showed 152 GB of DRAM reads per launch against 1.95 GB algorithmic.)
+    const double panel_bytes = (double)VQ_BM * D * 2.0;
+    auto panels_in_flight = [&](int ns) {
+      const int c = (sm_count + ns - 1) / ns;
+      return (double)(n_mblk < c ? n_mblk : c) * panel_bytes;
+    };
+    int ns_min = 1;
+    while (ns_min < VQ_NS_MAX && ns_min * 2 <= n_tiles && panels_in_flight(ns_min) > 64e6) ns_min *= 2;
+    // among the admissible split counts pick the one that fills the persistent grid most evenly
     double best_eff = 0.0;
-    for (int ns = 1; ns <= VQ_NS_MAX && ns <= n_tiles; ns *= 2) {
+    for (int ns = ns_min; ns <= VQ_NS_MAX && ns <= n_tiles; ns *= 2) {
       const long long items = (long long)n_mblk * ns;
       const long long rounds = (items + sm_count - 1) / sm_count;
       const double eff = (double)items / (double)(rounds * sm_count);

@@ -148,3 +148,29 @@ def test_real_audio_through_reference_api_golden(variant, mode):
     # the search is exact for the latents the kernels produced
     E = state_dict(variant)["quantizer.grvq.rvqs.0.layers.0._codebook.embed"][0]
     assert torch.equal(codes.cpu().reshape(-1), R.vq_search(xin.float().cpu().reshape(-1, xin.shape[-1]), E))
+
+
+def test_long_clip_interior_is_shift_invariant():
+    """Size-independent property for long inputs: the network has a finite receptive field (encoder +-60 frames,
+    decoder ~+-20: SURVEY section 5) and no global-in-time op, so the codes / waveform of a window cut out of a long
+    clip equal the long clip's in the window's interior.  Long clip: T = 4100 frames (43.7 s, ragged vs the
+    128-frame tiles), window = frames [1031, 3131)."""
+    eng = engine("W1", "bf16")
+    mel = make_mel(1, 4100, seed=77)
+    a0, a1, margin = 1031, 3131, 160
+    pipe_codes = []
+    wavs = []
+    for m in (mel, mel[:, :, a0:a1].contiguous()):
+        enc = eng.encoder(m.to(eng.device))
+        codes, _, _, quant = eng.quantizer(enc, want_fup=False)
+        pipe_codes.append(codes.cpu())
+        wavs.append(eng.generator(quant).cpu())
+    full_c, win_c = pipe_codes
+    full_w, win_w = wavs
+    assert full_w.shape == (1, 4100 * 256)
+    ci = slice(margin, (a1 - a0) - margin)
+    agree = (full_c[:, a0 + margin:a1 - margin] == win_c[:, ci]).float().mean().item()
+    assert agree == 1.0, agree
+    w_full = full_w[:, (a0 + margin) * 256:(a1 - margin) * 256]
+    w_win = win_w[:, margin * 256:((a1 - a0) - margin) * 256]
+    assert rel_err(w_win, w_full) < 1e-5
