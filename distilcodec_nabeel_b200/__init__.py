@@ -7,8 +7,9 @@ every entry point raises.
 """
 from . import _abi
 from .engine import Engine, load_config
-from .modules import B200Encoder, B200Generator, B200Quantizer, EngineSet, GRVQResult, build_modules, patch
+from .modules import (B200Encoder, B200Generator, B200MelSpectrogram, B200Quantizer, EngineSet, GRVQResult,
+                      build_modules, mel_buffers, patch)
 from .sharding import Pipeline, shard_clips, gather_by_clip
 
 __all__ = ["Engine", "EngineSet", "B200Encoder", "B200Quantizer", "B200Generator", "GRVQResult", "Pipeline",
-           "build_modules", "patch", "load_config", "shard_clips", "gather_by_clip", "_abi"]
+           "build_modules", "patch", "B200MelSpectrogram", "mel_buffers", "load_config", "shard_clips", "gather_by_clip", "_abi"]

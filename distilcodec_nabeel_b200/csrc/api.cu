@@ -39,7 +39,7 @@ int sm_count_of_current_device() {
 // ---------------------------------------------------------------------------------------------- profiler
 static const char* kProfNames[PC_COUNT] = {"gemm_tc", "gemm_f32", "vq_score", "vq_prep", "vq_rescore",
                                            "vq_exhaustive", "dwconv_ln", "layernorm", "cast", "gather",
-                                           "transpose", "conv_post_tanh", "prepack", "conv_ws"};
+                                           "transpose", "conv_post_tanh", "prepack", "conv_ws", "mel"};
 struct ProfRec {
   int cls;
   cudaEvent_t e0, e1;
@@ -163,6 +163,9 @@ struct dc_handle_s {
   __nv_bfloat16* codebook_bf16 = nullptr;
   float *c2 = nullptr, *c2max = nullptr;
   int K = 0, CD = 0;
+  // mel front-end
+  const float *mel_fb = nullptr, *mel_window = nullptr;
+  float* mel_twiddle = nullptr;
   // generator
   Dense conv_pre, ups[8], rb[8][3][2][3];
   float* post_w = nullptr;  // [k][C_last] (device copy)
@@ -709,7 +712,22 @@ int dc_finalize(dc_handle h, void* stream) {
   const bool has_enc = find_raw(h, "encoder.norm.weight") != nullptr;
   const bool has_q = find_raw(h, "quantizer.grvq.rvqs.0.project_in.weight") != nullptr;
   const bool has_gen = find_raw(h, "generator.conv_post.bias") != nullptr;
-  DC_CHECK(has_enc || has_q || has_gen, DC_ERR_STATE, "no weights set");
+  const bool has_mel = find_raw(h, "spec_transform.fb") != nullptr;
+  DC_CHECK(has_enc || has_q || has_gen || has_mel, DC_ERR_STATE, "no weights set");
+  h->mel_fb = h->mel_window = nullptr;
+  if (has_mel) {  // ---- log-mel front-end (models/mel_spec.py)
+    DC_GET_RAW(fb, "spec_transform.fb");
+    DC_GET_RAW(win, "spec_transform.spectrogram.window");
+    DC_CHECK(fb->shape.size() == 2 && fb->shape[0] == 513 && fb->shape[1] == 128 && win->numel == 1024, DC_ERR_SHAPE,
+             "mel front-end supports n_fft 1024 / 128 mels only (fb (513,128), window (1024))");
+    h->mel_fb = fb->d;
+    h->mel_window = win->d;
+    float tw[2048];
+    mel_twiddles_host(tw);
+    DC_TRY(dev_alloc(h, &h->mel_twiddle, (size_t)2048));
+    DC_CUDA(cudaMemcpyAsync(h->mel_twiddle, tw, sizeof(tw), cudaMemcpyHostToDevice, st));
+    DC_CUDA(cudaStreamSynchronize(st));
+  }
 
   if (has_enc) {  // ---- encoder (models/encoders.py:8-61)
     DC_TRY(pack_conv1d(h, "encoder.downsample_layers.0.0.", 1, &h->stem, st));
@@ -854,7 +872,7 @@ int dc_finalize(dc_handle h, void* stream) {
     RawTensor& t = it->second;
     // every >= 2-D tensor (incl. the (C,1,7) depthwise weights) now has a packed copy; a later dc_finalize()
     // therefore needs the full state_dict again
-    if (t.owned && t.shape.size() >= 2 && t.numel > 4096) {
+    if (t.owned && t.shape.size() >= 2 && t.numel > 4096 && it->first.compare(0, 15, "spec_transform.") != 0) {
       cudaFree(t.d);
       it = h->raw.erase(it);
     } else {
@@ -962,6 +980,15 @@ int dc_vq_search(dc_handle h, const void* x_dev, int x_is_bf16, const float* x2_
                           h->c2max, h->K, codes_dev, ws_dev ? ws : nullptr, ws_bytes > lost ? ws_bytes - lost : 0,
                           h->vq_window, h->vq_tc, h->vq_x2_exact, reinterpret_cast<cudaStream_t>(stream), h->sm_count,
                           stats_host);
+}
+
+int dc_mel_forward(dc_handle h, const float* audio_dev, int B, int Ls, float* mel_ncl_dev, void* stream) {
+  DC_API_BEGIN(h);
+  DC_NEED_FINAL(h);
+  DC_CHECK(h->mel_fb != nullptr, DC_ERR_STATE, "mel front-end buffers not loaded (spec_transform.fb / .spectrogram.window)");
+  DC_CHECK(audio_dev && mel_ncl_dev && B > 0 && Ls > 0, DC_ERR_ARG, "bad argument to dc_mel_forward");
+  return launch_mel(audio_dev, h->mel_window, h->mel_twiddle, h->mel_fb, mel_ncl_dev, B, Ls,
+                    reinterpret_cast<cudaStream_t>(stream));
 }
 
 int dc_ncl_to_nlc(const float* in_dev, float* out_dev, int B, int C, int T, void* stream) {
@@ -1106,7 +1133,7 @@ int dc_profile_collect(dc_profile_row* rows, int cap, int* n) {
 
 uint64_t dc_launch_count(void) {
   return g_launches_api + gemm_tc_launch_count() + gemm_f32_launch_count() + pointwise_launch_count() +
-         vq_launch_count() + conv_ws_launch_count();
+         vq_launch_count() + conv_ws_launch_count() + mel_launch_count();
 }
 
 }  // extern "C"

@@ -136,6 +136,12 @@ uint64_t vq_launch_count();
 uint64_t pointwise_launch_count();
 uint64_t gemm_f32_launch_count();
 
+// log-mel front-end (mel.cu): audio (B, Ls) fp32 -> log-mel (B, 128, T), T = (Ls - 256) / 256 + 1
+int launch_mel(const float* audio, const float* window /*[1024]*/, const float* twiddle /*[1024][2]*/,
+               const float* fb /*[513][128]*/, float* mel, int B, int Ls, cudaStream_t st);
+int mel_twiddles_host(float* out /*2 * 1024 floats*/);
+uint64_t mel_launch_count();
+
 int sm_count_of_current_device();
 
 // ---------------------------------------------------------------- per-kernel-class timing (bench.py's roofline)
@@ -143,7 +149,7 @@ int sm_count_of_current_device();
 // CUDA event pair on the launching stream and books the launch's ALGORITHMIC flops / HBM bytes.
 enum ProfClass {
   PC_GEMM_TC = 0, PC_GEMM_F32, PC_VQ_SCORE, PC_VQ_PREP, PC_VQ_RESCORE, PC_VQ_EXHAUSTIVE, PC_DWCONV_LN, PC_LAYERNORM,
-  PC_CAST, PC_GATHER, PC_TRANSPOSE, PC_CONV_POST, PC_PREPACK, PC_CONV_WS, PC_COUNT
+  PC_CAST, PC_GATHER, PC_TRANSPOSE, PC_CONV_POST, PC_PREPACK, PC_CONV_WS, PC_MEL, PC_COUNT
 };
 struct ProfScope {
   int idx = -1;

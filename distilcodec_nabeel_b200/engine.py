@@ -215,6 +215,19 @@ class Engine:
                                                          self._stream()), "dc_generator_forward")
         return wav
 
+    def mel(self, audio: torch.Tensor) -> torch.Tensor:
+        """audio (B, Ls) or (B, 1, Ls) fp32 on the device -> log-mel (B, 128, T) fp32 (models/mel_spec.py:109-122)."""
+        if audio.dim() == 3:
+            audio = audio.squeeze(1)
+        self._check_in(audio, torch.float32)
+        B, Ls = audio.shape
+        T = (Ls - 256) // 256 + 1
+        out = torch.empty(B, 128, T, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.dc_mel_forward(self.h, audio.data_ptr(), B, Ls, out.data_ptr(), self._stream()),
+                       "dc_mel_forward")
+        return out
+
     # ------------------------------------------------------------------------------------------ ops
     def vq_search(self, x: torch.Tensor, x2: Optional[torch.Tensor] = None, stats: bool = False):
         """Nearest-code search only.  x (N, 3584) bf16 or fp32; x2 optional fp32 (N,) row square-norms as the

@@ -206,6 +206,34 @@ class B200Generator(_Shim):
         return None
 
 
+def mel_buffers(cfg: dict) -> Dict[str, torch.Tensor]:
+    """The two non-persistent buffers of the reference's LogMelSpectrogram (models/mel_spec.py:24,85-98), built the
+    way the reference builds them, under the names the C ABI expects."""
+    import torchaudio.functional as AF
+    sc = cfg["spec_transform"]
+    fb = AF.melscale_fbanks(n_freqs=sc["n_fft"] // 2 + 1, f_min=float(sc["fmin"]),
+                            f_max=float(sc["fmax"] or sc["sampling_rate"] // 2), n_mels=sc["num_mels"],
+                            sample_rate=sc["sampling_rate"], norm="slaney", mel_scale="slaney")
+    return {"spec_transform.fb": fb, "spec_transform.spectrogram.window": torch.hann_window(sc["win_size"])}
+
+
+class B200MelSpectrogram(_Shim):
+    """models/mel_spec.py LogMelSpectrogram: forward(x[B,1,Ls] or [B,Ls]) -> log-mel [B,128,T], on the GPU (the
+    reference forces the STFT onto the CPU, mel_spec.py:39).  SURVEY.md section 8f, row f-1."""
+    prefix = "spec_transform."
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, return_linear: bool = False, sample_rate: Optional[int] = None):
+        if return_linear:
+            raise RuntimeError("return_linear is not on the inference path (only the log-mel is produced)")
+        sr = self._engines.config["spec_transform"]["sampling_rate"]
+        if sample_rate is not None and sample_rate != sr:
+            raise RuntimeError(f"resampling is not part of the hot path; pass {sr} Hz audio")
+        eng = self._engines.get()
+        x = x.to(eng.device, non_blocking=True).float()
+        return eng.mel(x.squeeze(1).contiguous() if x.dim() == 3 else x.contiguous())
+
+
 def build_modules(state_dict: Dict[str, torch.Tensor], device="cuda", config: Optional[dict] = None,
                   force_mode: Optional[str] = None, **engine_kwargs):
     """-> (encoder, quantizer, generator) shims sharing one EngineSet."""
@@ -216,10 +244,11 @@ def build_modules(state_dict: Dict[str, torch.Tensor], device="cuda", config: Op
     return B200Encoder(es), B200Quantizer(es), B200Generator(es)
 
 
-def patch(codec, device=None, force_mode: Optional[str] = None, **engine_kwargs):
+def patch(codec, device=None, force_mode: Optional[str] = None, mel_frontend: bool = False, **engine_kwargs):
     """Install the B200 hot path on a reference `DistilCodec` instance (after construction / `from_pretrained`):
     replaces `codec.encoder`, `codec.quantizer`, `codec.generator` (distil_codec.py:52-54) and leaves everything
-    else — the class, its methods, the CPU mel front-end — untouched.  Returns the codec."""
+    else — the class, its methods, the CPU mel front-end — untouched.  `mel_frontend=True` additionally replaces
+    `codec.spec_transform` (distil_codec.py:56-63) by the GPU log-mel kernel.  Returns the codec."""
     sd = OrderedDict()
     for name in ("encoder", "quantizer", "generator"):
         mod = getattr(codec, name, None)
@@ -230,7 +259,13 @@ def patch(codec, device=None, force_mode: Optional[str] = None, **engine_kwargs)
     if device is None:
         device = getattr(codec, "device", None) or "cuda"
     cfg = getattr(codec, "codec_config", None)  # the dict DistilCodec was constructed from (distil_codec.py:41)
+    st = getattr(codec, "spec_transform", None)
+    if mel_frontend and st is not None:  # the module's own (non-persistent) buffers
+        sd["spec_transform.fb"] = st.fb.detach()
+        sd["spec_transform.spectrogram.window"] = st.spectrogram.window.detach()
     enc, q, gen = build_modules(sd, device, cfg, force_mode, **engine_kwargs)
+    if mel_frontend and st is not None:
+        codec.spec_transform = B200MelSpectrogram(enc._engines)
     codec.encoder = enc
     codec.quantizer = q
     if getattr(codec, "generator", None) is not None:

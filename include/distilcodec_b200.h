@@ -130,6 +130,14 @@ int dc_quantizer_decode(dc_handle h, const int64_t* codes_dev, int B, int T, flo
 int dc_generator_forward(dc_handle h, const float* z_nlc_dev, int B, int T, float* wav_dev, void* ws_dev,
                          size_t ws_bytes, void* stream);
 
+/* spec_transform(audios): LogMelSpectrogram.forward, models/mel_spec.py:109-122 -> LinearSpectrogram.forward :26-57
+ * (call sites distil_codec.py:138,191; the reference forces this stage onto the CPU, mel_spec.py:39).  Needs the two
+ * non-persistent buffers of that module, handed over with dc_set_tensor under the names `spec_transform.fb`
+ * (513, 128) and `spec_transform.spectrogram.window` (1024); n_fft 1024 / hop 256 / 128 mels only.
+ *   audio_dev   : fp32 (B, Ls) mono samples exactly as the reference passes them (already left-padded by one zero)
+ *   mel_ncl_dev : fp32 (B, 128, T), T = (Ls - 256) / 256 + 1 (integer division) */
+int dc_mel_forward(dc_handle h, const float* audio_dev, int B, int Ls, float* mel_ncl_dev, void* stream);
+
 /* Layout helpers between the reference's channels-first tensors and the ABI's channels-last ones. */
 int dc_ncl_to_nlc(const float* in_dev, float* out_dev, int B, int C, int T, void* stream);
 int dc_nlc_to_ncl(const float* in_dev, float* out_dev, int B, int T, int C, void* stream);

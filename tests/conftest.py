@@ -61,10 +61,12 @@ _ENGINES = {}
 
 def engine(variant: str, mode: str, codebook_size=None):
     """Session-cached Engine (C-ABI handle) on cuda:0.  Raises (never falls back) if the library is missing."""
-    from distilcodec_nabeel_b200 import Engine
+    from distilcodec_nabeel_b200 import Engine, load_config, mel_buffers
     key = (variant, mode, codebook_size)
     if key not in _ENGINES:
-        _ENGINES[key] = Engine(state_dict(variant, codebook_size), 0, mode)
+        sd = dict(state_dict(variant, codebook_size))
+        sd.update(mel_buffers(load_config()))          # the front-end's two non-persistent buffers (fb, window)
+        _ENGINES[key] = Engine(sd, 0, mode)
     return _ENGINES[key]
 
 

@@ -105,3 +105,17 @@ def test_forward_pieces_and_decode_layouts(codecs):
         cb = torch.cat([q0.codes, q0.codes.flip(2)], 0)                       # (2,1,T,1)
         zb = patched.quantizer.decode(cb)
         assert zb.shape == (2, 1024, q0.codes.shape[2]) and torch.allclose(zb[0:1], z0, atol=1e-5)
+
+
+def test_mel_frontend_patch_and_buffers(codecs):
+    """patch(..., mel_frontend=True) swaps spec_transform too; mel_buffers() rebuilds the reference's two
+    non-persistent buffers (models/mel_spec.py:24,85-98) bit-for-bit."""
+    from distilcodec_nabeel_b200 import B200MelSpectrogram, load_config, mel_buffers, patch
+    ref, _ = codecs
+    bufs = mel_buffers(load_config())
+    assert torch.equal(bufs["spec_transform.fb"], ref.spec_transform.fb)
+    assert torch.equal(bufs["spec_transform.spectrogram.window"], ref.spec_transform.spectrogram.window)
+    sd = state_dict("W1", 1024)
+    c = patch(ref_loader.build_reference_codec(sd, codebook_size=1024), device="cpu", mel_frontend=True)
+    assert isinstance(c.spec_transform, B200MelSpectrogram)
+    assert "spec_transform.fb" in c.encoder._engines.state_dict
