@@ -39,12 +39,12 @@ int sm_count_of_current_device() {
 // ---------------------------------------------------------------------------------------------- profiler
 static const char* kProfNames[PC_COUNT] = {"gemm_tc", "gemm_f32", "vq_score", "vq_prep", "vq_rescore",
                                            "vq_exhaustive", "dwconv_ln", "layernorm", "cast", "gather",
-                                           "transpose", "conv_post_tanh", "prepack", "conv_ws", "mel"};
+                                           "transpose", "conv_post_tanh", "prepack", "conv_ws", "mel", "conv_ts"};
 struct ProfRec {
   int cls;
   cudaEvent_t e0, e1;
   double flops, bytes;
-  char shape[40];
+  char shape[56];
 };
 static thread_local bool g_prof_on = false;
 static thread_local std::vector<ProfRec> g_prof_recs;
@@ -1104,8 +1104,18 @@ int dc_profile_collect(dc_profile_row* rows, int cap, int* n) {
       set_error("dc_profile_collect: event timing failed: %s", cudaGetErrorString(cudaGetLastError()));
       rc = DC_ERR_CUDA;
     }
+    // shape = "<template config>|layer shape": the kernel instantiation is part of the class name (what ncu lists
+    // as one kernel), the layer shape goes in brackets
     std::string key = kProfNames[r.cls];
-    if (r.shape[0]) key += std::string("[") + r.shape + "]";
+    if (r.shape[0]) {
+      std::string sh(r.shape);
+      const size_t bar = sh.find('|');
+      if (bar != std::string::npos) {
+        key += sh.substr(0, bar);
+        sh = sh.substr(bar + 1);
+      }
+      key += "[" + sh + "]";
+    }
     auto it = agg.find(key);
     if (it == agg.end()) {
       dc_profile_row row;
@@ -1133,7 +1143,7 @@ int dc_profile_collect(dc_profile_row* rows, int cap, int* n) {
 
 uint64_t dc_launch_count(void) {
   return g_launches_api + gemm_tc_launch_count() + gemm_f32_launch_count() + pointwise_launch_count() +
-         vq_launch_count() + conv_ws_launch_count() + mel_launch_count();
+         vq_launch_count() + conv_ws_launch_count() + mel_launch_count() + conv_ts_launch_count();
 }
 
 }  // extern "C"

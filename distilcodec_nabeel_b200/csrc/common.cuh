@@ -101,6 +101,11 @@ bool conv_ws_supported(const ConvGemmShape& s);
 int launch_conv_ws(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
                    cudaStream_t st, int sm_count);
 uint64_t conv_ws_launch_count();
+// tap-shared 256-row-tile variant for C = N = 128 (conv_ts.cu); same operands as launch_gemm_tc
+bool conv_ts_supported(const ConvGemmShape& s);
+int launch_conv_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
+                   cudaStream_t st, int sm_count);
+uint64_t conv_ts_launch_count();
 
 // pointwise / bandwidth-bound kernels (pointwise.cu)
 int launch_transpose_ncl_to_nlc(const float* in, void* out, int out_dt, int B, int C, int T, cudaStream_t st);
@@ -149,7 +154,7 @@ int sm_count_of_current_device();
 // CUDA event pair on the launching stream and books the launch's ALGORITHMIC flops / HBM bytes.
 enum ProfClass {
   PC_GEMM_TC = 0, PC_GEMM_F32, PC_VQ_SCORE, PC_VQ_PREP, PC_VQ_RESCORE, PC_VQ_EXHAUSTIVE, PC_DWCONV_LN, PC_LAYERNORM,
-  PC_CAST, PC_GATHER, PC_TRANSPOSE, PC_CONV_POST, PC_PREPACK, PC_CONV_WS, PC_MEL, PC_COUNT
+  PC_CAST, PC_GATHER, PC_TRANSPOSE, PC_CONV_POST, PC_PREPACK, PC_CONV_WS, PC_MEL, PC_CONV_TS, PC_COUNT
 };
 struct ProfScope {
   int idx = -1;

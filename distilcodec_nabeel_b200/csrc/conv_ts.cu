@@ -1,0 +1,222 @@
+// Tap-shared tcgen05 implicit-GEMM convolution for the C = 128 decoder stage (ResBlock1 convs of HiFiGAN stage 2,
+// models/convnext_utils.py:106-113, and the C = 128 ConvTranspose1d, models/generators.py:67-79).
+//
+//   out[b,t,n] = epi( sum_{j<J} sum_{c<128} A[b, t + shift0 + j*dil, c] * W[n, j*128 + c] )          N = 128
+//
+// Why a third kernel: with C = N = 128 the generic kernel (gemm_tc.cu) moves 32 KB from L2 per 256 tensor-pipe
+// cycles and SM (the activation rows once per tap, the weights once per 128-row tile) = ~25 TB/s chip-wide, more
+// than L2 delivers; it ran at 570 TFLOP/s.  Here
+//   * a tile is 256 output rows (two M = 128 accumulators that share every weight tile), and
+//   * per 64-channel chunk the 256 + (J-1)*dil activation rows are loaded ONCE (two TMA boxes of 160 rows) and all J
+//     taps read them through row-shifted UMMA descriptors (legal for swizzled tiles: scripts/desc_probe.cu),
+// which cuts the L2 traffic per MAC 3.3x (k = 11) and leaves the layer bound by the tensor pipe / HBM.
+// Weights are too large to keep resident (J * 32 KB), they stream through a 5-stage ring of 16 KB (tap, chunk) tiles.
+// TMEM: 2 tiles x 2 halves x 128 columns = all 512 columns; 16 epilogue warps, group g drains half g of every tile.
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include "epilogue.cuh"
+
+namespace dc {
+
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, int swizzle_bytes);
+
+static thread_local uint64_t g_launches_ts = 0;
+uint64_t conv_ts_launch_count() { return g_launches_ts; }
+
+namespace ts {
+constexpr int C = 128, N = 128, BK = 64, KCH = C / BK;  // two 64-channel chunks
+constexpr int BOX_ROWS = 160, A_ROWS = 2 * BOX_ROWS;    // 320 >= 256 + max halo (56)
+constexpr int A_BYTES = A_ROWS * BK * 2;                // 40 KB per chunk buffer
+constexpr int B_BYTES = N * BK * 2;                     // 16 KB per (tap, chunk) weight tile
+constexpr int B_STAGES = 5;
+constexpr int STG_BYTES = 16 * 32 * 32 * 4;             // 16 epilogue warps x (32 rows x 32 fp32)
+constexpr int A_OFF = 0, B_OFF = KCH * A_BYTES, STG_OFF = B_OFF + B_STAGES * B_BYTES, BAR_OFF = STG_OFF + STG_BYTES;
+constexpr int TOTAL = BAR_OFF + 256 + 1024;
+constexpr int THREADS = 64 + 16 * 32;
+static_assert(TOTAL <= 232448, "shared memory budget");
+}  // namespace ts
+
+__global__ void __launch_bounds__(ts::THREADS, 1)
+conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvGemmShape s,
+               Epilogue ep, int variant, int tiles_per_clip, int total_tiles) {
+  using namespace ts;
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, N);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem + A_OFF;
+  uint8_t* sB = smem + B_OFF;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem + BAR_OFF);  // [KCH]
+  uint64_t* aempty = afull + KCH;                                  // [KCH]
+  uint64_t* bfull = aempty + KCH;                                  // [B_STAGES]
+  uint64_t* bempty = bfull + B_STAGES;                             // [B_STAGES]
+  uint64_t* tfull = bempty + B_STAGES;                             // [2]
+  uint64_t* tempty = tfull + 2;                                    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < KCH; ++i) {
+        ptx::mbar_init(&afull[i], 1);
+        ptx::mbar_init(&aempty[i], 1);
+      }
+      for (int i = 0; i < B_STAGES; ++i) {
+        ptx::mbar_init(&bfull[i], 1);
+        ptx::mbar_init(&bempty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&tfull[i], 1);
+        ptx::mbar_init(&tempty[i], 16);
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<512>(tmem_slot);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (same order as the MMA issuer consumes)
+    if (lane == 0) {
+      int bs = 0;
+      uint32_t bphase = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int clip = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * 256;
+        for (int kc = 0; kc < KCH; ++kc) {
+          ptx::mbar_wait(&aempty[kc], aphase ^ 1);
+          ptx::mbar_expect_tx(&afull[kc], A_BYTES);
+          ptx::tma_load_3d(sA + kc * A_BYTES, &tmA, &afull[kc], kc * BK, t0 + s.shift0, clip);
+          ptx::tma_load_3d(sA + kc * A_BYTES + BOX_ROWS * BK * 2, &tmA, &afull[kc], kc * BK, t0 + s.shift0 + BOX_ROWS,
+                           clip);
+          for (int j = 0; j < s.J; ++j) {
+            ptx::mbar_wait(&bempty[bs], bphase ^ 1);
+            ptx::mbar_expect_tx(&bfull[bs], B_BYTES);
+            ptx::tma_load_2d(sB + bs * B_BYTES, &tmW, &bfull[bs], j * C + kc * BK, 0);
+            if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
+          }
+        }
+        aphase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      int bs = 0, it = 0;
+      uint32_t bphase = 0, aphase = 0;
+      const uint32_t tap_step = (uint32_t)(s.dil * BK * 2) >> 4;   // descriptor start-address units (16 B) per tap
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int p = it & 1;
+        ptx::mbar_wait(&tempty[p], ((it >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d0 = tmem_base + p * (2 * N), d1 = d0 + N;
+        for (int kc = 0; kc < KCH; ++kc) {
+          ptx::mbar_wait(&afull[kc], aphase);
+          ptx::tc_fence_after();
+          uint64_t da = ptx::make_smem_desc<128>(ptx::smem_u32(sA + kc * A_BYTES));
+          for (int j = 0; j < s.J; ++j) {
+            ptx::mbar_wait(&bfull[bs], bphase);
+            ptx::tc_fence_after();
+            const uint64_t db = ptx::make_smem_desc<128>(ptx::smem_u32(sB + bs * B_BYTES));
+            const uint32_t acc = (kc | j) != 0 ? 1u : 0u;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              ptx::mma_bf16_ss(d0, da + 2 * k, db + 2 * k, IDESC, acc | (uint32_t)(k != 0));
+              ptx::mma_bf16_ss(d1, da + (128 * BK * 2 >> 4) + 2 * k, db + 2 * k, IDESC, acc | (uint32_t)(k != 0));
+            }
+            ptx::mma_commit(&bempty[bs]);
+            if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
+            da += tap_step;  // tap j + 1 = the same rows, dil rows further down
+          }
+          ptx::mma_commit(&aempty[kc]);
+        }
+        ptx::mma_commit(&tfull[p]);
+        aphase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: group g (8 warps) drains half g of every tile
+    float* stg = reinterpret_cast<float*>(smem + STG_OFF) + (warp - 2) * (32 * 32);
+    const int g = (warp - 2) >> 3;
+    const int wg = 2 + ((warp - 2) & 7);  // warp id within the group (2..9): wg % 4 == warp % 4 = TMEM lane quarter
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int clip = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * 256;
+      const int p = it & 1;
+      ptx::mbar_wait(&tfull[p], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      epilogue_tile<N>(ep, variant, stg, tmem_base + p * (2 * N) + g * N, clip, t0 + g * 128, 0, s.T, wg, lane);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[p]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+bool conv_ts_supported(const ConvGemmShape& s) {
+  return s.C == ts::C && s.N == ts::N && 256 + (s.J - 1) * s.dil <= ts::A_ROWS && s.J >= 1;
+}
+
+int launch_conv_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
+                   cudaStream_t st, int sm_count) {
+  using namespace ts;
+  DC_CHECK(conv_ts_supported(s), DC_ERR_SHAPE, "conv_ts: unsupported shape C=%d N=%d J=%d dil=%d", s.C, s.N, s.J, s.dil);
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  DC_CUDA(cudaGetDevice(&dev));
+  if (!(attr_dev_mask & (1 << dev))) {
+    DC_CUDA(cudaFuncSetAttribute(conv_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
+    attr_dev_mask |= 1 << dev;
+  }
+  const int tiles_per_clip = (s.T + 255) / 256;
+  const long long total = (long long)s.B * tiles_per_clip;
+  DC_CHECK(total > 0 && total < (1ll << 31), DC_ERR_SHAPE, "conv_ts: bad tile count");
+  CUtensorMap tmA, tmW;
+  {
+    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)s.T, (uint64_t)s.B};
+    const uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)s.T * C * 2};
+    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BOX_ROWS, 1};
+    DC_TRY(make_tmap_bf16(&tmA, A, 3, dims, strides, box, 128));
+  }
+  {
+    const uint64_t K = (uint64_t)s.J * C;
+    const uint64_t dims[2] = {K, (uint64_t)N};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)N};
+    DC_TRY(make_tmap_bf16(&tmW, W, 2, dims, strides, box, 128));
+  }
+  const int grid = (int)(total < sm_count ? total : sm_count);
+  {
+    const double rows = (double)s.B * s.T;
+    const double macs = rows * N * s.J * C * s.alg_scale;
+    const int esig = (e.act ? 1 : 0) | (e.gamma ? 2 : 0) | (e.res ? 4 : 0) | (e.add1 ? 8 : 0) |
+                     (e.out0 ? (e.out0_dt == DT_F32 ? 16 : 32) : 0) | (e.out1 ? 32 : 0);
+    const double out_bytes = (e.out0 ? (e.out0_dt == DT_F32 ? 4.0 : 2.0) : 0.0) + (e.out1 ? 2.0 : 0.0) +
+                             (e.res ? 4.0 : 0.0) + (e.add1 ? 8.0 : 0.0);
+    ProfScope ps(PC_CONV_TS, 2.0 * macs, rows * C * 2.0 + (double)N * s.J * C * 2.0 + rows * N * out_bytes, st,
+                 "|C%d N%d J%d d%d e%d", C, N, s.J, s.dil, esig);
+    conv_ts_kernel<<<grid, THREADS, TOTAL, st>>>(tmA, tmW, s, e, epilogue_variant(e), tiles_per_clip, (int)total);
+  }
+  ++g_launches_ts;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+}  // namespace dc

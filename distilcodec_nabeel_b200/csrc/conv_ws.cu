@@ -225,7 +225,7 @@ static int launch_ws(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvG
     const double out_bytes = (e.out0 ? (e.out0_dt == DT_F32 ? 4.0 : 2.0) : 0.0) + (e.out1 ? 2.0 : 0.0) +
                              (e.res ? 4.0 : 0.0) + (e.add1 ? 8.0 : 0.0);
     ProfScope ps(PC_CONV_WS, 2.0 * macs, rows * C * 2.0 + (double)N * s.J * C * 2.0 + rows * N * out_bytes, st,
-                 "C%d N%d J%d d%d e%d", C, N, s.J, s.dil, esig);
+                 "<%d,%d>|C%d N%d J%d d%d e%d", C, N, C, N, s.J, s.dil, esig);
     conv_ws_kernel<C, N><<<grid, kWsThreads, lay.total, st>>>(tmA, tmW, s, e, epilogue_variant(e), lay, tiles_per_clip,
                                                               (int)total);
   }

@@ -262,7 +262,7 @@ static int launch_cfg(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
     const double out_bytes = (e.out0 ? (e.out0_dt == DT_F32 ? 4.0 : 2.0) : 0.0) + (e.out1 ? 2.0 : 0.0) +
                              (e.res ? 4.0 : 0.0) + (e.add1 ? 8.0 : 0.0);
     ProfScope ps(PC_GEMM_TC, 2.0 * macs, rows * s.C * 2.0 + (double)s.N * s.J * s.C * 2.0 + rows * s.N * out_bytes, st,
-                 "C%d N%d J%d d%d e%d", s.C, s.N, s.J, s.dil, esig);
+                 "<%d,%d,%d,%d,%d>|C%d N%d J%d d%d e%d", BN, BK, STAGES, EG, ACC, s.C, s.N, s.J, s.dil, esig);
     gemm_tc_kernel<BN, BK, STAGES, EG, ACC><<<grid, L::THREADS, L::TOTAL, st>>>(
         tmA, tmB, s, e, epilogue_variant(e), tiles_per_clip, (int)m_tiles, n_tiles);
   }
@@ -283,6 +283,7 @@ int launch_gemm_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGem
     s.B = 1;
   }
   if (conv_ws_supported(s)) return launch_conv_ws(A, W, s, e, st, sm_count);  // narrow decoder stages
+  if (conv_ts_supported(s)) return launch_conv_ts(A, W, s, e, st, sm_count);  // C = N = 128 decoder stage
   if (s.C % 64 != 0) {
     DC_CHECK(s.N % 32 == 0, DC_ERR_SHAPE, "gemm_tc: unsupported N for C=32");
     if (s.N % 64 == 0) return launch_cfg<64, 32, 8>(A, W, s, e, st, sm_count);
@@ -295,6 +296,9 @@ int launch_gemm_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGem
     // longer K or two N tiles the shallower operand ring loses more than the epilogue gains)
     if ((e.res || (e.out0 && e.out1)) && s.J * s.C <= 1792 && s.N == 256)
       return launch_cfg<256, 64, 3, 2, 2>(A, W, s, e, st, sm_count);
+    // the ConvNeXt MLP's first GEMM: K = C <= 1024 (6-8k MMA cycles per tile) against a 128 x 256 GELU + bf16
+    // epilogue of similar length -> two epilogue groups as well
+    if (e.act == ACT_GELU && s.J * s.C <= 1024) return launch_cfg<256, 64, 3, 2, 2>(A, W, s, e, st, sm_count);
     return launch_cfg<256, 64, 4>(A, W, s, e, st, sm_count);
   }
   if (s.N % 128 == 0) {

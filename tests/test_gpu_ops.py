@@ -35,7 +35,9 @@ CONV_CASES = [
     (2, 140, 1024, 1024, 13, 1, 0, False), # conv_pre k13
     (2, 300, 512, 512, 3, 5, 2, False),    # ResBlock conv k3 d5 + SiLU
     (2, 300, 256, 256, 11, 5, 0, True),    # ResBlock conv k11 d5 (+-25 halo) + residual
-    (1, 515, 128, 128, 7, 3, 2, False),
+    (1, 515, 128, 128, 7, 3, 2, False),    # C = N = 128: tap-shared 256-row tiles (conv_ts)
+    (3, 300, 128, 128, 11, 5, 0, True),    # ... largest halo (+-25), residual, several clips, ragged second tile
+    (2, 256, 128, 128, 3, 1, 2, False),
     (2, 700, 64, 64, 11, 1, 0, True),
     (2, 1000, 32, 32, 3, 1, 2, False),     # C = 32 stage (64-byte swizzle tiles)
     (1, 1, 1024, 3584, 1, 1, 0, False),    # project_in, a single frame
