@@ -174,3 +174,21 @@ def test_long_clip_interior_is_shift_invariant():
     w_full = full_w[:, (a0 + margin) * 256:(a1 - margin) * 256]
     w_win = win_w[:, margin * 256:((a1 - a0) - margin) * 256]
     assert rel_err(w_win, w_full) < 1e-5
+
+
+@pytest.mark.parametrize("T", [1, 3])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_tiny_clips_all_stages(T, mode):
+    """Clips far shorter than any tile (T = 1 frame = 256 samples): every TMA box is mostly out of bounds."""
+    sd = state_dict("W1")
+    eng = engine("W1", mode)
+    mel = make_mel(2, T, seed=90 + T)
+    enc = eng.encoder(mel.to(eng.device))
+    tol_enc = TOL_ENC_W1_BF16 if mode == "bf16" else TOL[mode]
+    assert rel_err(enc.transpose(1, 2), R.encoder_forward(sd, mel)) < tol_enc
+    codes, xin, _, quant = eng.quantizer(enc, want_fup=False)
+    E = sd["quantizer.grvq.rvqs.0.layers.0._codebook.embed"][0]
+    assert torch.equal(codes.cpu().reshape(-1), R.vq_search(xin.float().cpu().reshape(-1, xin.shape[-1]), E))
+    wav = eng.generator(quant)
+    ref = R.generator_forward(sd, quant.transpose(1, 2).cpu())[:, 0]
+    assert wav.shape == (2, 256 * T) and rel_err(wav, ref) < TOL[mode]
