@@ -6,12 +6,13 @@
 // Why a third kernel: with C = N = 128 the generic kernel (gemm_tc.cu) moves 32 KB from L2 per 256 tensor-pipe
 // cycles and SM (the activation rows once per tap, the weights once per 128-row tile) = ~25 TB/s chip-wide, more
 // than L2 delivers; it ran at 570 TFLOP/s.  Here
-//   * a tile is 256 output rows (two M = 128 accumulators that share every weight tile), and
+//   * a tile is 256 output rows (one weight tile feeds 256 rows), and
 //   * per 64-channel chunk the 256 + (J-1)*dil activation rows are loaded ONCE (two TMA boxes of 160 rows) and all J
 //     taps read them through row-shifted UMMA descriptors (legal for swizzled tiles: scripts/desc_probe.cu),
 // which cuts the L2 traffic per MAC 3.3x (k = 11) and leaves the layer bound by the tensor pipe / HBM.
 // Weights are too large to keep resident (J * 32 KB), they stream through a 5-stage ring of 16 KB (tap, chunk) tiles.
-// TMEM: 2 tiles x 2 halves x 128 columns = all 512 columns; 16 epilogue warps, group g drains half g of every tile.
+// The weight tile is the MMA's A operand (M = 128 channels) and the 256 rows its B operand (N = 256): see the kernel.
+// TMEM: 2 tiles x 256 columns (time rows) x 128 lanes (channels) = all 512 columns; 16 epilogue warps.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -42,7 +43,11 @@ __global__ void __launch_bounds__(ts::THREADS, 1)
 conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvGemmShape s,
                Epilogue ep, int variant, int tiles_per_clip, int total_tiles) {
   using namespace ts;
-  constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, N);
+  // Operand roles are swapped: the WEIGHT tile (128 output channels x 64) is the MMA's A operand (M = 128) and the
+  // 256 activation rows are its B operand (N = 256), so the accumulator is transposed (TMEM lane = channel, column
+  // = time row).  An M = 128, N = 128 MMA reads 8 KB of shared memory per 64 tensor cycles = the full 128 B/clk of
+  // the shared-memory port; M = 128, N = 256 reads 12 KB per 128 cycles = 96 B/clk and is no longer operand-bound.
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, 256);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem + A_OFF;
@@ -119,7 +124,7 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int p = it & 1;
         ptx::mbar_wait(&tempty[p], ((it >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d0 = tmem_base + p * (2 * N), d1 = d0 + N;
+        const uint32_t d0 = tmem_base + p * 256;
         for (int kc = 0; kc < KCH; ++kc) {
           ptx::mbar_wait(&afull[kc], aphase);
           ptx::tc_fence_after();
@@ -130,10 +135,8 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t db = ptx::make_smem_desc<128>(ptx::smem_u32(sB + bs * B_BYTES));
             const uint32_t acc = (kc | j) != 0 ? 1u : 0u;
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              ptx::mma_bf16_ss(d0, da + 2 * k, db + 2 * k, IDESC, acc | (uint32_t)(k != 0));
-              ptx::mma_bf16_ss(d1, da + (128 * BK * 2 >> 4) + 2 * k, db + 2 * k, IDESC, acc | (uint32_t)(k != 0));
-            }
+            for (int k = 0; k < BK / 16; ++k)  // D[channel, row] += W[channel, k] * A[row + j*dil, k]
+              ptx::mma_bf16_ss(d0, db + 2 * k, da + 2 * k, IDESC, acc | (uint32_t)(k != 0));
             ptx::mma_commit(&bempty[bs]);
             if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
             da += tap_step;  // tap j + 1 = the same rows, dil rows further down
@@ -145,17 +148,17 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue: group g (8 warps) drains half g of every tile
+    // ------------------------------------------------------------ epilogue: 16 warps = 4 channel quarters x 4 row quarters
     float* stg = reinterpret_cast<float*>(smem + STG_OFF) + (warp - 2) * (32 * 32);
-    const int g = (warp - 2) >> 3;
-    const int wg = 2 + ((warp - 2) & 7);  // warp id within the group (2..9): wg % 4 == warp % 4 = TMEM lane quarter
+    // epilogue warp index whose low 2 bits equal the hardware warp's TMEM lane quarter (warp % 4)
+    const int warp16 = (((warp - 2) >> 2) << 2) | (warp & 3);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int clip = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * 256;
       const int p = it & 1;
       ptx::mbar_wait(&tfull[p], (it >> 1) & 1);
       ptx::tc_fence_after();
-      epilogue_tile<N>(ep, variant, stg, tmem_base + p * (2 * N) + g * N, clip, t0 + g * 128, 0, s.T, wg, lane);
+      epilogue_tile_transposed(ep, variant, stg, tmem_base + p * 256, clip, t0, s.T, warp16, lane);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[p]);

@@ -113,7 +113,7 @@ __device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, const float4 v) {
 
 // One 32-row x CW-column chunk of one warp.  stg: the warp's XOR-swizzled transpose tile (already written);
 // off0: element offset (row * ldo + n) of this lane's first row group; nvalid: row groups of this lane with t < T.
-template <int V, int CW>
+template <int V, int CW, bool LINEAR = false /* staging tile written un-swizzled (transposed accumulators) */>
 __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, const float* stg, int lane, size_t off0,
                                                int nvalid, const float4 b4, const float4 g4) {
   constexpr int CPR = CW / 4, RPI = 32 / CPR, NG = 32 / RPI;
@@ -133,7 +133,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, const float* 
 #pragma unroll
   for (int k = 0; k < NG; ++k) {
     const int r = k * RPI + rsub;
-    const int rswz = CW == 32 ? (r & 7) : ((r >> 1) & 3);
+    const int rswz = LINEAR ? 0 : (CW == 32 ? (r & 7) : ((r >> 1) & 3));
     float4 v = *reinterpret_cast<const float4*>(stg + r * CW + ((cg ^ rswz) << 2));
     if (k < nvalid) {
       const size_t off = off0 + k * stride;
@@ -167,7 +167,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, const float* 
 }
 
 // generic (runtime-flag) chunk
-template <int CW>
+template <int CW, bool LINEAR = false>
 __device__ __forceinline__ void epilogue_chunk_generic(const Epilogue& ep, const float* stg, int lane, size_t off0,
                                                        int nvalid, int n, const float4 b4, const float4 g4) {
   constexpr int CPR = CW / 4, RPI = 32 / CPR, NG = 32 / RPI;
@@ -180,19 +180,35 @@ __device__ __forceinline__ void epilogue_chunk_generic(const Epilogue& ep, const
 #pragma unroll
   for (int k = 0; k < NG; ++k) {
     const int r = k * RPI + rsub;
-    const int rswz = CW == 32 ? (r & 7) : ((r >> 1) & 3);
+    const int rswz = LINEAR ? 0 : (CW == 32 ? (r & 7) : ((r >> 1) & 3));
     const float4 v = *reinterpret_cast<const float4*>(stg + r * CW + ((cg ^ rswz) << 2));
     if (k < nvalid) epilogue4(ep, (off0 + k * stride - n) / ep.ldo, n, v, b4, g4, r4[k]);
+  }
+}
+
+template <int CW, bool LINEAR>
+__device__ __forceinline__ void epilogue_dispatch(const Epilogue& ep, int variant, const float* stg, int lane,
+                                                  size_t off0, int nvalid, int n, const float4 b4, const float4 g4) {
+  switch (variant) {
+    case EV_SILU_BF16: epilogue_chunk<EV_SILU_BF16, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_RES_F32_BF16S: epilogue_chunk<EV_RES_F32_BF16S, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_RES_F32: epilogue_chunk<EV_RES_F32, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_RES_MEAN_BF16S: epilogue_chunk<EV_RES_MEAN_BF16S, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_F32_BF16S: epilogue_chunk<EV_F32_BF16S, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_GELU_BF16: epilogue_chunk<EV_GELU_BF16, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_GAMMA_RES_F32: epilogue_chunk<EV_GAMMA_RES_F32, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_F32: epilogue_chunk<EV_F32, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_BF16: epilogue_chunk<EV_BF16, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    default: epilogue_chunk_generic<CW, LINEAR>(ep, stg, lane, off0, nvalid, n, b4, g4); break;
   }
 }
 
 // One 128 x BN output tile: the 8 epilogue warps (CTA warps 2..9) each take a TMEM lane quarter (rows) and one half of
 // the columns.  TMEM -> registers (thread = row) -> XOR-swizzled per-warp smem tile -> (lane = 4 columns) -> global.
 // tmem_acc: TMEM address (lane 0) of the tile's accumulator; stg: this warp's 32 x CW fp32 transpose buffer.
-template <int BN>
+template <int BN, int CW = (BN >= 64 ? 32 : 16) /* chunk width in columns */>
 __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int variant, float* stg, uint32_t tmem_acc, int clip,
                                               int t0, int n0, int T, int warp, int lane) {
-  constexpr int CW = BN >= 64 ? 32 : 16;  // chunk width in columns
   constexpr int CPR = CW / 4;             // 16-byte column groups per row (8 or 4)
   constexpr int RPI = 32 / CPR;           // rows covered by one warp-wide access (4 or 8)
   const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -219,18 +235,39 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int variant, f
     const int tb = t0 + q * 32 + rsub;  // first row of this lane
     const int nvalid = min(32 / RPI, max(0, (T - tb + RPI - 1) / RPI));
     const size_t off0 = ((size_t)clip * T + tb) * (size_t)ep.ldo + n;
-    switch (variant) {
-      case EV_SILU_BF16: epilogue_chunk<EV_SILU_BF16, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
-      case EV_RES_F32_BF16S: epilogue_chunk<EV_RES_F32_BF16S, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
-      case EV_RES_F32: epilogue_chunk<EV_RES_F32, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
-      case EV_RES_MEAN_BF16S: epilogue_chunk<EV_RES_MEAN_BF16S, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
-      case EV_F32_BF16S: epilogue_chunk<EV_F32_BF16S, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
-      case EV_GELU_BF16: epilogue_chunk<EV_GELU_BF16, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
-      case EV_GAMMA_RES_F32: epilogue_chunk<EV_GAMMA_RES_F32, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
-      case EV_F32: epilogue_chunk<EV_F32, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
-      case EV_BF16: epilogue_chunk<EV_BF16, CW>(ep, stg, lane, off0, nvalid, b4, g4); break;
-      default: epilogue_chunk_generic<CW>(ep, stg, lane, off0, nvalid, n, b4, g4); break;
-    }
+    epilogue_dispatch<CW, false>(ep, variant, stg, lane, off0, nvalid, n, b4, g4);
+    __syncwarp();
+  }
+}
+
+// Transposed accumulator (conv_ts.cu): TMEM lanes = output channels, TMEM columns = time rows of a 256-row tile.
+// The 16 epilogue warps split the tile as (4 channel quarters) x (4 row quarters of 64); a warp's chunk is 32
+// channels x 32 rows: thread = channel writes its 32 row values as scalar stores stg[row][channel] (consecutive
+// lanes -> consecutive words, conflict-free), after which the tile has the same [row][column] form as above.
+// tmem_acc: TMEM address (lane 0, first column) of the tile's accumulator; warp16: epilogue warp index 0..15 whose
+// (warp16 % 4) equals the hardware warp's TMEM lane quarter.
+__device__ __forceinline__ void epilogue_tile_transposed(const Epilogue& ep, int variant, float* stg, uint32_t tmem_acc,
+                                                         int clip, int t0, int T, int warp16, int lane) {
+  constexpr int CW = 32, RPI = 4;
+  const int q = warp16 & 3;       // channel quarter = TMEM lane quarter
+  const int rq = warp16 >> 2;     // row quarter: rows [64 rq, 64 rq + 64)
+  const int cg = lane & 7, rsub = lane >> 3;
+  const int n = q * 32 + cg * 4;
+  const float4 b4 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 g4 = ep.gamma ? __ldg(reinterpret_cast<const float4*>(ep.gamma + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    const int r0 = rq * 64 + c * 32;  // first time row of this chunk within the tile
+    uint32_t acc[32];
+    ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + r0, acc);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) stg[i * CW + lane] = __uint_as_float(acc[i]);
+    __syncwarp();
+    const int tb = t0 + r0 + rsub;
+    const int nvalid = min(32 / RPI, max(0, (T - tb + RPI - 1) / RPI));
+    const size_t off0 = ((size_t)clip * T + tb) * (size_t)ep.ldo + n;
+    epilogue_dispatch<CW, true>(ep, variant, stg, lane, off0, nvalid, n, b4, g4);
     __syncwarp();
   }
 }

@@ -77,7 +77,8 @@ template <int BN, int BK, int STAGES, int EG = 1>
 struct GemmTcSmem {
   static constexpr int A_BYTES = 128 * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int CW = BN >= 64 ? 32 : 16;               // columns per epilogue chunk (each warp owns BN/2)
+  // columns per epilogue chunk (each warp owns BN/2); 16 where two epilogue groups must fit beside a 4-stage ring
+  static constexpr int CW = (BN >= 64 && !(BN == 256 && EG == 2 && STAGES == 4)) ? 32 : 16;
   static constexpr int STG_OFF = STAGES * (A_BYTES + B_BYTES);  // 8 warps x (32 rows x CW fp32) transpose buffers
   static constexpr int STG_BYTES = EG * 8 * 32 * CW * 4;
   static constexpr int THREADS = 64 + EG * 256;
@@ -200,7 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t aphase = (it / ACC) & 1;
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
-      epilogue_tile<BN>(ep, variant, stg, tmem_base + as * BN, clip, t0, n0, s.T, wg, lane);
+      epilogue_tile<BN, L::CW>(ep, variant, stg, tmem_base + as * BN, clip, t0, n0, s.T, wg, lane);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[as]);
@@ -296,6 +297,9 @@ int launch_gemm_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGem
     // longer K or two N tiles the shallower operand ring loses more than the epilogue gains)
     if ((e.res || (e.out0 && e.out1)) && s.J * s.C <= 1792 && s.N == 256)
       return launch_cfg<256, 64, 3, 2, 2>(A, W, s, e, st, sm_count);
+    // longer K with a residual epilogue: keep the 4-stage operand ring and fit the second epilogue group by halving
+    // the transpose chunks (16 columns, 2 KB per warp)
+    if (e.res || (e.out0 && e.out1)) return launch_cfg<256, 64, 4, 2, 2>(A, W, s, e, st, sm_count);
     // the ConvNeXt MLP's first GEMM: K = C <= 1024 (6-8k MMA cycles per tile) against a 128 x 256 GELU + bf16
     // epilogue of similar length -> two epilogue groups as well
     if (e.act == ACT_GELU && s.J * s.C <= 1024) return launch_cfg<256, 64, 3, 2, 2>(A, W, s, e, st, sm_count);
