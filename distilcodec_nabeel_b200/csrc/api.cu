@@ -111,6 +111,8 @@ struct RawTensor {
 struct Dense {  // one shifted-row implicit GEMM layer
   int C = 0, J = 1, shift0 = 0, dil = 1, N = 0;
   float alg_scale = 1.f;            // true MACs / executed MACs (ConvTranspose1d phase GEMMs pad taps with zeros)
+  int phase_cols = 0;               // ConvTranspose1d: output columns per stride phase
+  uint32_t zero_taps = 0;           // bit (phase*J + j): tap j is all-zero for that phase
   __nv_bfloat16* w_bf16 = nullptr;  // [N][J*C]   (DC_MODE_BF16)
   float* w_f32 = nullptr;           // [J*C][N]   (DC_MODE_FP32)
   const float* bias = nullptr;      // [N]
@@ -236,10 +238,13 @@ static int pack_dense(dc_handle_s* h, const float* src, bool transposed, int O, 
     pd.s_c = (long long)O * k;
     pd.s_k = 1;
     DC_CHECK(stride * d->J <= 128, DC_ERR_SHAPE, "conv-transpose tap table too large");
+    d->phase_cols = O;
+    d->zero_taps = 0;
     for (int ph = 0; ph < stride; ++ph)
       for (int j = 0; j < d->J; ++j) {
         const int kk = ph + pad - (sh_min + j) * stride;
         pd.kmap[ph * d->J + j] = (kk >= 0 && kk < k) ? kk : -1;
+        if (!(kk >= 0 && kk < k) && stride * d->J <= 32) d->zero_taps |= 1u << (ph * d->J + j);
       }
   }
   d->C = I;
@@ -317,7 +322,7 @@ static int pack_block(dc_handle_s* h, const std::string& p, Block* blk, cudaStre
 
 // ---- layer runners --------------------------------------------------------------------------------------
 static int run_dense(const dc_handle_s* h, const Dense& d, const void* A, int B, int T, Epilogue ep, cudaStream_t st) {
-  ConvGemmShape s{B, T, d.C, d.J, d.shift0, d.dil, d.N, d.alg_scale};
+  ConvGemmShape s{B, T, d.C, d.J, d.shift0, d.dil, d.N, d.alg_scale, d.phase_cols, d.zero_taps};
   if (!ep.bias) ep.bias = d.bias;
   ep.ldo = d.N;
   if (h->mode == DC_MODE_BF16)

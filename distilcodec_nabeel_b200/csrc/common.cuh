@@ -43,6 +43,11 @@ enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
 struct ConvGemmShape {
   int B, T, C, J, shift0, dil, N;
   float alg_scale = 1.f;  // algorithmic / executed MACs (< 1 for ConvTranspose1d phase GEMMs with zero-padded taps)
+  // ConvTranspose1d phase GEMMs: output columns [ph*phase_cols, (ph+1)*phase_cols) belong to stride phase ph, and
+  // bit (ph*J + j) of zero_taps says that tap j's weights are all zero for that phase (the tap is skipped when a
+  // whole N tile lies inside one phase)
+  int phase_cols = 0;
+  uint32_t zero_taps = 0;
 };
 
 // Runtime epilogue, applied per output element v = acc:

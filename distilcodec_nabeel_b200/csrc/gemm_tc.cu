@@ -70,6 +70,12 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
 
 namespace dc {
 
+// taps (bit j) whose weights are all zero for the N tile [n0, n0 + bn): only when the tile lies inside one stride phase
+__device__ __forceinline__ uint32_t tile_zero_taps(const ConvGemmShape& s, int n0, int bn) {
+  if (s.zero_taps == 0 || s.phase_cols % bn != 0) return 0;
+  return (s.zero_taps >> ((n0 / s.phase_cols) * s.J)) & ((1u << s.J) - 1u);
+}
+
 // ---------------------------------------------------------------- the kernel
 // warp 0 TMA, warp 1 MMA, then EG groups of 8 epilogue warps; group g takes the tiles with (tile counter % EG) == g.
 // EG = 2 (with ACC = 4 TMEM accumulators) is used where the epilogue is an HBM latency chain (C = 128 decoder stage).
@@ -136,7 +142,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int total_tiles = m_tiles * n_tiles;
   const int kchunks = s.C / BK;
-  const int num_kb = s.J * kchunks;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -146,7 +151,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int clip = m_blk / tiles_per_clip, t0 = (m_blk % tiles_per_clip) * 128, n0 = n_blk * BN;
+        const uint32_t skip = tile_zero_taps(s, n0, BN);
         for (int j = 0; j < s.J; ++j) {
+          if ((skip >> j) & 1u) continue;  // all-zero tap of this stride phase (ConvTranspose1d)
           const int trow = t0 + s.shift0 + j * s.dil;
           for (int kc = 0; kc < kchunks; ++kc) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
@@ -170,7 +177,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::mbar_wait(&tempty[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int n0m = (tile % n_tiles) * BN;
+        const int live_kb = (s.J - __popc(tile_zero_taps(s, n0m, BN))) * kchunks;  // the producer skips zero taps
+        for (int kb = 0; kb < live_kb; ++kb) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(sA + stage * L::A_BYTES);
