@@ -15,6 +15,28 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Sum 8 independent values over the 32 lanes with 9 shuffles instead of 8 x 5: each butterfly step also halves the
+// set of values a lane is responsible for.  On return lane L holds the warp-wide total of v[((L >> 2) & 7) bit-
+// reversed appropriately]: row index r(L) = ((L >> 4) & 1) * 4 + ((L >> 3) & 1) * 2 + ((L >> 2) & 1).
+__device__ __forceinline__ float warp_sum8(const float (&v)[8], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float a[4], b[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b4 ? v[i] : v[i + 4], keep = b4 ? v[i + 4] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b3 ? a[i] : a[i + 2], keep = b3 ? a[i + 2] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float c = (b2 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, b2 ? b[0] : b[1], 4);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  return c;
+}
+
 // ------------------------------------------------------------------------------------------ transposes
 // (B, C, T) fp32 -> (B, T, C) fp32|bf16 ; 32x32 tiles through padded shared memory, coalesced both ways.
 template <typename TOut>
@@ -147,7 +169,11 @@ __global__ void __launch_bounds__(C / 4) dwconv_ln_run_kernel(const float* __res
   // prefetching costs 32 registers: at C = 1024 (256 threads) that halves the resident blocks and loses more than
   // it gains (measured 2.7 vs 3.4 TB/s); below that it wins (C = 768: 3.7 vs 3.1 TB/s)
   constexpr bool PREFETCH = C <= 768;
-  __shared__ float red[2][R][NW];
+  static_assert(R == 8, "warp_sum8 reduces 8 rows at once");
+  __shared__ __align__(16) float red[2][R][8];  // [pass][row][warp], padded to 8 warps (unused slots stay 0)
+  for (int i = threadIdx.x; i < 2 * R * 8; i += C / 4) (&red[0][0][0])[i] = 0.f;
+  __syncthreads();
+  const int my_row = ((threadIdx.x >> 4) & 1) * 4 + ((threadIdx.x >> 3) & 1) * 2 + ((threadIdx.x >> 2) & 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = tid * 4;
   const int t_begin = blockIdx.x * run, t_end = min(T, t_begin + run);
@@ -186,48 +212,48 @@ __global__ void __launch_bounds__(C / 4) dwconv_ln_run_kernel(const float* __res
     float s[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      float4 a = bias;
+      float2 lo = make_float2(bias.x, bias.y), hi = make_float2(bias.z, bias.w);
 #pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        a.x = fmaf(x[r + j].x, w[j].x, a.x); a.y = fmaf(x[r + j].y, w[j].y, a.y);
-        a.z = fmaf(x[r + j].z, w[j].z, a.z); a.w = fmaf(x[r + j].w, w[j].w, a.w);
+      for (int j = 0; j < 7; ++j) {  // packed fp32 FMA: 14 FFMA2 instead of 28 FFMA per row
+        lo = ffma2(make_float2(x[r + j].x, x[r + j].y), make_float2(w[j].x, w[j].y), lo);
+        hi = ffma2(make_float2(x[r + j].z, x[r + j].w), make_float2(w[j].z, w[j].w), hi);
       }
-      y[r] = a;
-      s[r] = warp_sum((a.x + a.y) + (a.z + a.w));
+      y[r] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      const float2 sm = fadd2(lo, hi);
+      s[r] = sm.x + sm.y;
     }
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) red[0][r][warp] = s[r];
+    {
+      const float tot = warp_sum8(s, lane);
+      if ((lane & 3) == 0) red[0][my_row][warp] = tot;
     }
     __syncthreads();
     float mean[R], q[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      float m = 0.f;
-#pragma unroll
-      for (int k = 0; k < NW; ++k) m += red[0][r][k];
-      mean[r] = m * (1.f / C);
-      const float dx = y[r].x - mean[r], dy = y[r].y - mean[r], dz = y[r].z - mean[r], dw = y[r].w - mean[r];
-      q[r] = warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw));
+      const float4 p0 = *reinterpret_cast<const float4*>(&red[0][r][0]), p1 = *reinterpret_cast<const float4*>(&red[0][r][4]);
+      mean[r] = (((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w))) * (1.f / C);
+      const float2 nm = make_float2(-mean[r], -mean[r]);
+      const float2 dl = fadd2(make_float2(y[r].x, y[r].y), nm), dh = fadd2(make_float2(y[r].z, y[r].w), nm);
+      y[r] = make_float4(dl.x, dl.y, dh.x, dh.y);  // keep the centred values
+      const float2 sq = ffma2(dh, dh, fmul2(dl, dl));
+      q[r] = sq.x + sq.y;
     }
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) red[1][r][warp] = q[r];
+    {
+      const float tot = warp_sum8(q, lane);
+      if ((lane & 3) == 0) red[1][my_row][warp] = tot;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      float v = 0.f;
-#pragma unroll
-      for (int k = 0; k < NW; ++k) v += red[1][r][k];
+      const float4 p0 = *reinterpret_cast<const float4*>(&red[1][r][0]), p1 = *reinterpret_cast<const float4*>(&red[1][r][4]);
+      const float v = ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w));
       const float rstd = rsqrtf(v * (1.f / C) + 1e-6f);
       const int t = t0 + r;
       if (t < t_end) {
-        float4 o;
-        o.x = (y[r].x - mean[r]) * rstd * gw.x + gb.x;
-        o.y = (y[r].y - mean[r]) * rstd * gw.y + gb.y;
-        o.z = (y[r].z - mean[r]) * rstd * gw.z + gb.z;
-        o.w = (y[r].w - mean[r]) * rstd * gw.w + gb.w;
+        const float2 rs = make_float2(rstd, rstd);
+        const float2 ol = ffma2(fmul2(make_float2(y[r].x, y[r].y), rs), make_float2(gw.x, gw.y), make_float2(gb.x, gb.y));
+        const float2 oh = ffma2(fmul2(make_float2(y[r].z, y[r].w), rs), make_float2(gw.z, gw.w), make_float2(gb.z, gb.w));
+        const float4 o = make_float4(ol.x, ol.y, oh.x, oh.y);
         if constexpr (sizeof(TOut) == 4) {
           *reinterpret_cast<float4*>(ob + (size_t)t * C) = o;
         } else {
@@ -249,7 +275,7 @@ __global__ void __launch_bounds__(C / 4) dwconv_ln_run_kernel(const float* __res
 template <int C>
 static int dwconv_ln_run_dispatch(const float* in, const float* dw_w, const float* dw_b, const float* ln_w,
                                   const float* ln_b, void* out, int out_dt, int B, int T, cudaStream_t st) {
-  const int run = 64;
+  const int run = 64;  // rows per block (6 halo rows are re-read per run; 128 measured slower: fewer, longer blocks)
   dim3 grid((T + run - 1) / run, B);
   ProfScope ps(PC_DWCONV_LN, 0, (double)B * T * C * (4.0 + (out_dt == DT_F32 ? 4.0 : 2.0)), st, "C%d", C);
   if (out_dt == DT_F32)
