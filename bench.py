@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine tunable key=value (dc_set_option), repeatable")
     ap.add_argument("--cpu-clips", type=int, default=2, help="bounded CPU-baseline sample: clips of --cpu-seconds")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
@@ -201,6 +202,9 @@ def main():
     sd = weights.make_state_dict("W0")
     eng = Engine(sd, local, args.mode, workspace_limit_bytes=64 << 30)
     del sd
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, float(v))
     pipe = Pipeline(eng)
     # two alternating synthetic batches (bit-identical on every machine: numpy Philox), kept on host (pinned) and in HBM
     base = make_mel(8, T, seed=100 + rank)

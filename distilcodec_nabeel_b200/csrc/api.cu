@@ -150,6 +150,7 @@ struct dc_handle_s {
   float vq_window = 0.25f;
   bool vq_tc = true;
   bool vq_x2_exact = false;
+  bool fuse_pairs = true;
 
   // encoder
   Dense stem;
@@ -178,6 +179,7 @@ struct dc_handle_s {
 
 namespace dc {
 
+static int run_dense(const dc_handle_s* h, const struct Dense& d, const void* A, int B, int T, Epilogue ep, cudaStream_t st);
 static int act_dt(const dc_handle_s* h) { return h->mode == DC_MODE_BF16 ? DT_BF16 : DT_F32; }
 static size_t act_es(const dc_handle_s* h) { return h->mode == DC_MODE_BF16 ? 2 : 4; }
 
@@ -328,6 +330,26 @@ static int run_dense(const dc_handle_s* h, const Dense& d, const void* A, int B,
   if (h->mode == DC_MODE_BF16)
     return launch_gemm_tc(reinterpret_cast<const __nv_bfloat16*>(A), d.w_bf16, s, ep, st, h->sm_count);
   return launch_gemm_f32(reinterpret_cast<const float*>(A), d.w_f32, s, ep, st);
+}
+
+// One ResBlock1 step (convnext_utils.py:109-112): ep2( c2( silu( c1(S) + b1 ) ) ).  In bf16 mode the narrow stages
+// run it as ONE kernel (conv_ws.cu, conv1's output stays in shared memory); otherwise two implicit GEMMs through `tb`.
+static int run_conv_pair(const dc_handle_s* h, const Dense& c1, const Dense& c2, const void* S, void* tb, int B, int T,
+                         Epilogue e2, cudaStream_t st) {
+  ConvGemmShape s1{B, T, c1.C, c1.J, c1.shift0, c1.dil, c1.N, c1.alg_scale, c1.phase_cols, c1.zero_taps};
+  ConvGemmShape s2{B, T, c2.C, c2.J, c2.shift0, c2.dil, c2.N, c2.alg_scale, c2.phase_cols, c2.zero_taps};
+  if (h->mode == DC_MODE_BF16 && h->fuse_pairs && c1.bias && conv_ws_pair_supported(s1, s2)) {
+    if (!e2.bias) e2.bias = c2.bias;
+    e2.ldo = c2.N;
+    return launch_conv_ws_pair(reinterpret_cast<const __nv_bfloat16*>(S), c1.w_bf16, c2.w_bf16, c1.bias, s1, s2, e2, st,
+                               h->sm_count);
+  }
+  Epilogue e1;  // xt = silu(c1(silu(x)))
+  e1.act = ACT_SILU;
+  e1.out0 = tb;
+  e1.out0_dt = act_dt(h);
+  DC_TRY(run_dense(h, c1, S, B, T, e1, st));
+  return run_dense(h, c2, tb, B, T, e2, st);
 }
 
 // x (fp32, B*T x C) <- x + gamma * pw2(gelu(pw1(LN(dwconv(x)))))     (convnext_utils.py:263-282)
@@ -537,12 +559,7 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
         const float* cur_x = x;
         const void* cur_s = sx;
         for (int n3 = 0; n3 < 3; ++n3) {
-          Epilogue e1;  // xt = silu(c1(silu(x)))
-          e1.act = ACT_SILU;
-          e1.out0 = tb;
-          e1.out0_dt = ad;
-          DC_TRY(run_dense(h, h->rb[i][b][0][n3], cur_s, B, L, e1, st));
-          Epilogue e2;  // x = c2(xt) + x
+          Epilogue e2;  // x = c2(silu(c1(silu(x)))) + x
           e2.res = cur_x;
           e2.res_dt = DT_F32;
           if (n3 < 2) {
@@ -561,7 +578,7 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
             e2.out1 = carry[cur ^ 1];
             e2.out1_dt = ad;
           }
-          DC_TRY(run_dense(h, h->rb[i][b][1][n3], tb, B, L, e2, st));
+          DC_TRY(run_conv_pair(h, h->rb[i][b][0][n3], h->rb[i][b][1][n3], cur_s, tb, B, L, e2, st));
           cur_x = X[b];
           cur_s = sb;
         }
@@ -667,6 +684,8 @@ int dc_set_option(dc_handle h, const char* key, double value) {
     h->vq_tc = value != 0.0;
   } else if (!strcmp(key, "vq_x2_exact")) {
     h->vq_x2_exact = value != 0.0;
+  } else if (!strcmp(key, "fuse_pairs")) {
+    h->fuse_pairs = value != 0.0;
   } else {
     set_error("unknown option '%s'", key);
     return DC_ERR_ARG;

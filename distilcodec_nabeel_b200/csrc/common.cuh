@@ -137,6 +137,11 @@ bool conv_ws_supported(const ConvGemmShape& s);
 int launch_conv_ws(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
                    cudaStream_t st, int sm_count);
 uint64_t conv_ws_launch_count();
+// fused ResBlock step  out = epi2(conv2(silu(conv1(S) + bias1))): conv1's output stays in shared memory
+bool conv_ws_pair_supported(const ConvGemmShape& s1, const ConvGemmShape& s2);
+int launch_conv_ws_pair(const __nv_bfloat16* S, const __nv_bfloat16* W1, const __nv_bfloat16* W2, const float* bias1,
+                        const ConvGemmShape& s1, const ConvGemmShape& s2, const Epilogue& e2, cudaStream_t st,
+                        int sm_count);
 // tap-shared 256-row-tile variant for C = N = 128 (conv_ts.cu); same operands as launch_gemm_tc
 bool conv_ts_supported(const ConvGemmShape& s);
 int launch_conv_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,

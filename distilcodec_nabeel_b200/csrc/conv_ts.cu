@@ -93,7 +93,7 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (same order as the MMA issuer consumes)
-    if (lane == 0) {
+    if (ptx::elect_one()) {  // one lane, known to the compiler: operands go to uniform registers
       int bs = 0;
       uint32_t bphase = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -116,7 +116,7 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    if (ptx::elect_one()) {  // one lane, known to the compiler: operands go to uniform registers
       int bs = 0, it = 0;
       uint32_t bphase = 0, aphase = 0;
       const uint32_t tap_step = (uint32_t)(s.dil * BK * 2) >> 4;   // descriptor start-address units (16 B) per tap

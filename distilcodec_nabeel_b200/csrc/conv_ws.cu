@@ -101,7 +101,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(wbar, (uint32_t)lay.w_bytes);
       for (int j = 0; j < s.J; ++j) ptx::tma_load_2d(sW + j * W_TAP_BYTES, &tmW, wbar, j * C, 0);
       int stage = 0;
@@ -116,8 +116,9 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (single thread; elect.sync tells the
+    // compiler that exactly one lane is active, so operands move to uniform registers without a waterfall loop)
+    if (ptx::elect_one()) {
       ptx::mbar_wait(wbar, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -177,6 +178,328 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::tc_fence_after();
     ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
   }
+}
+
+// ================================================================================================ fused conv pair
+// One ResBlock1 step  x' = conv2(silu(conv1(s) + b1)) + b2 + x   (models/convnext_utils.py:109-112, s = silu(x) from
+// the previous epilogue) in ONE kernel: conv1's output never goes to HBM.  Unfused, the pair moves 16 B per element
+// (conv1: 2 in + 2 out, conv2: 2 + 4 in, 4 + 2 out) and conv1 alone costs as much time as conv2 because its narrow
+// MMAs are bound by shared-memory operand reads; fused it moves 12 B and conv1's MMAs hide under conv2's HBM time.
+//
+// Tile = 128 rows of t = silu(conv1 + b1) -> 128 - (J-1) valid output rows of conv2 (its taps read t rows r .. r+J-1).
+//   warp 0        TMA: one box of 128 + (J-1)*dil rows of s per tile (both weight sets are loaded once per CTA)
+//   warp 1        MMA: conv1(i+1) is issued before conv2(i), so the tensor pipe works while epilogue 1 of tile i runs
+//   warps 2..5    epilogue 1: D1 (TMEM) -> +b1 -> SiLU -> bf16 -> the t tile in shared memory, written directly in
+//                 the UMMA K-major swizzled layout (128B/64B swizzle = XOR of the 16-byte chunk index with the row
+//                 bits) and zeroed outside [0, T) (conv2's zero padding applies to t); fence.proxy.async; arrive
+//   warps 6..21   epilogue 2, two groups of 8 warps on alternate tiles (group g owns accumulator D2[g]): the usual
+//                 fused epilogue (residual, dual store / 3-branch mean) -> global; it is the HBM latency chain of
+//                 the kernel, so it gets two tiles in flight, epilogue 1 (no global traffic) gets 4 warps
+constexpr int kPairE1Warps = 4, kPairE2Warps = 16;
+constexpr int kPairThreads = 64 + 32 * (kPairE1Warps + kPairE2Warps);
+
+struct PairLayout {
+  int w_bytes /*one weight set*/, a_stage_bytes, stages, t_bytes, a_off, t_off, stg_off, bar_off, total;
+};
+static PairLayout pair_layout(int C, int J, int RA) {
+  PairLayout l;
+  l.w_bytes = J * C * C * 2;
+  l.a_stage_bytes = (RA * C * 2 + 1023) / 1024 * 1024;
+  l.t_bytes = 144 * C * 2;  // 128 rows + the (J-1) <= 12 rows conv2's last taps touch (never valid outputs), 1024-aligned
+  const int stg_bytes = kPairE2Warps * 32 * 16 * 4 + 256;  // 16-column transpose chunks + conv1's bias
+  const int fixed = 2 * l.w_bytes + 2 * l.t_bytes + stg_bytes + 256 + 1024;
+  l.stages = (232448 - fixed) / l.a_stage_bytes;
+  if (l.stages > 6) l.stages = 6;
+  l.a_off = 2 * l.w_bytes;
+  l.t_off = l.a_off + (l.stages > 0 ? l.stages : 0) * l.a_stage_bytes;
+  l.stg_off = l.t_off + 2 * l.t_bytes;
+  l.bar_off = l.stg_off + stg_bytes;
+  l.total = l.bar_off + 256 + 1024;
+  return l;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kPairThreads, 1)
+conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
+                    const __grid_constant__ CUtensorMap tmW2, int T, int J, int dil, int shift_a /*tile row 0 of s
+                    relative to the first output row*/, const float* __restrict__ bias1, Epilogue ep, int variant,
+                    PairLayout lay, int tiles_per_clip, int total_tiles) {
+  constexpr int SW = C * 2, PITCH = C * 2;
+  constexpr int TMEM_COLS = 4 * C;  // D1[2], D2[2]
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, C);
+  constexpr int W_TAP_BYTES = C * C * 2;
+  const int MO = 128 - (J - 1), p2 = (J - 1) / 2;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW1 = smem;
+  uint8_t* sW2 = smem + lay.w_bytes;
+  uint8_t* sA = smem + lay.a_off;
+  uint8_t* sT = smem + lay.t_off;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem + lay.bar_off);  // [6]
+  uint64_t* aempty = afull + 6;                                        // [6]
+  uint64_t* d1full = aempty + 6;                                       // [2]
+  uint64_t* d1empty = d1full + 2;                                      // [2]
+  uint64_t* tfull = d1empty + 2;                                       // [2]  t tile written by epilogue 1
+  uint64_t* tempty = tfull + 2;                                        // [2]  t tile consumed by conv2's MMAs
+  uint64_t* d2full = tempty + 2;                                       // [2]
+  uint64_t* d2empty = d2full + 2;                                      // [2]
+  uint64_t* wbar = d2empty + 2;                                        // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int stages = lay.stages;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW1);
+    ptx::prefetch_tmap(&tmW2);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < 6; ++i) {
+        ptx::mbar_init(&afull[i], 1);
+        ptx::mbar_init(&aempty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&d1full[i], 1);
+        ptx::mbar_init(&d1empty[i], kPairE1Warps);
+        ptx::mbar_init(&tfull[i], kPairE1Warps);
+        ptx::mbar_init(&tempty[i], 1);
+        ptx::mbar_init(&d2full[i], 1);
+        ptx::mbar_init(&d2empty[i], 8);
+      }
+      ptx::mbar_init(wbar, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
+  if (threadIdx.x < C)  // conv1's bias, read by epilogue 1 for every tile
+    reinterpret_cast<float*>(smem + lay.stg_off + kPairE2Warps * 32 * 16 * 4)[threadIdx.x] = bias1[threadIdx.x];
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_d1 = tmem_base, tm_d2 = tmem_base + 2 * C;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(wbar, (uint32_t)(2 * lay.w_bytes));
+      for (int j = 0; j < J; ++j) {
+        ptx::tma_load_2d(sW1 + j * W_TAP_BYTES, &tmW1, wbar, j * C, 0);
+        ptx::tma_load_2d(sW2 + j * W_TAP_BYTES, &tmW2, wbar, j * C, 0);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t a_bytes = (uint32_t)(((128 + (J - 1) * dil + 7) / 8 * 8) * PITCH);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int clip = tile / tiles_per_clip, o0 = (tile % tiles_per_clip) * MO;
+        ptx::mbar_wait(&aempty[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&afull[stage], a_bytes);
+        ptx::tma_load_3d(sA + stage * lay.a_stage_bytes, &tmA, &afull[stage], 0, o0 + shift_a, clip);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer: conv1(0), then [conv1(i+1), conv2(i)]...
+    if (ptx::elect_one()) {
+      ptx::mbar_wait(wbar, 0);
+      const uint64_t w1_desc = ptx::make_smem_desc<SW>(ptx::smem_u32(sW1));
+      const uint64_t w2_desc = ptx::make_smem_desc<SW>(ptx::smem_u32(sW2));
+      const uint32_t a_step = (uint32_t)(dil * PITCH) >> 4, t_step = (uint32_t)PITCH >> 4;
+      int n_my = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) ++n_my;
+      int stage = 0;
+      uint32_t phase = 0;
+      auto conv1 = [&](int i) {
+        const int b = i & 1;
+        ptx::mbar_wait(&d1empty[b], ((i >> 1) & 1) ^ 1);
+        ptx::mbar_wait(&afull[stage], phase);
+        ptx::tc_fence_after();
+        uint64_t da = ptx::make_smem_desc<SW>(ptx::smem_u32(sA + stage * lay.a_stage_bytes));
+        uint64_t dw = w1_desc;
+        uint32_t accum = 0;
+        for (int j = 0; j < J; ++j) {
+#pragma unroll
+          for (int k = 0; k < C / 16; ++k) {
+            ptx::mma_bf16_ss(tm_d1 + b * C, da + 2 * k, dw + 2 * k, IDESC, accum);
+            accum = 1;
+          }
+          da += a_step;
+          dw += W_TAP_BYTES >> 4;
+        }
+        ptx::mma_commit(&aempty[stage]);
+        ptx::mma_commit(&d1full[b]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      };
+      auto conv2 = [&](int i) {
+        const int b = i & 1;
+        ptx::mbar_wait(&d2empty[b], ((i >> 1) & 1) ^ 1);
+        ptx::mbar_wait(&tfull[b], (i >> 1) & 1);
+        ptx::tc_fence_after();
+        uint64_t dt = ptx::make_smem_desc<SW>(ptx::smem_u32(sT + b * lay.t_bytes));
+        uint64_t dw = w2_desc;
+        uint32_t accum = 0;
+        for (int j = 0; j < J; ++j) {  // conv2 tap j reads t rows r + j
+#pragma unroll
+          for (int k = 0; k < C / 16; ++k) {
+            ptx::mma_bf16_ss(tm_d2 + b * C, dt + 2 * k, dw + 2 * k, IDESC, accum);
+            accum = 1;
+          }
+          dt += t_step;
+          dw += W_TAP_BYTES >> 4;
+        }
+        ptx::mma_commit(&tempty[b]);
+        ptx::mma_commit(&d2full[b]);
+      };
+      if (n_my > 0) conv1(0);
+      for (int i = 0; i < n_my; ++i) {
+        if (i + 1 < n_my) conv1(i + 1);
+        conv2(i);
+      }
+    }
+  } else if (warp < 2 + kPairE1Warps) {
+    // ------------------------------------------------------------ epilogue 1: D1 -> silu(. + b1) -> bf16 t tile in smem
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                       // t-tile row of this thread (4 warps x 32 rows, all columns)
+    const int swz = C >= 64 ? (row & 7) : ((row >> 1) & 3);
+    const float* sb1 = reinterpret_cast<const float*>(smem + lay.stg_off + kPairE2Warps * 32 * 16 * 4);
+    int i = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+      const int o0 = (tile % tiles_per_clip) * MO;
+      const int b = i & 1;
+      const int gt = o0 - p2 + row;                      // sequence position of this t row
+      const bool inside = gt >= 0 && gt < T;
+      ptx::mbar_wait(&d1full[b], (i >> 1) & 1);
+      ptx::tc_fence_after();
+      ptx::mbar_wait(&tempty[b], ((i >> 1) & 1) ^ 1);    // conv2 of tile i-2 has finished reading this t buffer
+      uint8_t* trow = sT + b * lay.t_bytes + row * PITCH;
+#pragma unroll
+      for (int c = 0; c < C / 32; ++c) {
+        uint32_t acc[32];
+        ptx::tmem_ld_32x32(tm_d1 + b * C + ((uint32_t)(q * 32) << 16) + c * 32, acc);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {                    // 8 columns = one 16-byte chunk of the bf16 row
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 bb = *reinterpret_cast<const float2*>(sb1 + c * 32 + g * 8 + 2 * e);
+            float v0 = __uint_as_float(acc[g * 8 + 2 * e]) + bb.x;
+            float v1 = __uint_as_float(acc[g * 8 + 2 * e + 1]) + bb.y;
+            v0 = inside ? silu_fast(v0) : 0.f;
+            v1 = inside ? silu_fast(v1) : 0.f;
+            __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          const int chunk = c * 4 + g;
+          *reinterpret_cast<uint4*>(trow + ((chunk ^ swz) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async();                          // generic-proxy smem writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&tfull[b]);
+        ptx::mbar_arrive(&d1empty[b]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue 2: D2 -> fused epilogue -> global
+    const int e2w = warp - (2 + kPairE1Warps);  // 0..15
+    const int group = e2w >> 3;
+    const int wg = 2 + (e2w & 7);               // 2..9 with wg % 4 == warp % 4 (TMEM lane quarter)
+    float* stg = reinterpret_cast<float*>(smem + lay.stg_off) + e2w * (32 * 16);
+    int i = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+      if ((i & 1) != group) continue;           // group g owns accumulator D2[g]
+      const int clip = tile / tiles_per_clip, o0 = (tile % tiles_per_clip) * MO;
+      const int b = i & 1;
+      ptx::mbar_wait(&d2full[b], (i >> 1) & 1);
+      ptx::tc_fence_after();
+      epilogue_tile<C, 16>(ep, variant, stg, tm_d2 + b * C, clip, o0, 0, T, wg, lane, o0 + MO);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&d2empty[b]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// s1: conv1 (dilated), s2: conv2 (dil 1); both C -> C with the same kernel size
+bool conv_ws_pair_supported(const ConvGemmShape& s1, const ConvGemmShape& s2) {
+  if (!(s1.C == s2.C && s1.N == s1.C && s2.N == s2.C && (s1.C == 32 || s1.C == 64))) return false;
+  if (s1.J != s2.J || s2.dil != 1 || s1.J < 2 || s1.J > 13 || (s1.J & 1) == 0) return false;
+  if (s1.shift0 != -s1.dil * (s1.J - 1) / 2 || s2.shift0 != -(s2.J - 1) / 2) return false;
+  if (s1.B != s2.B || s1.T != s2.T) return false;
+  const int RA = (128 + (s1.J - 1) * s1.dil + 7) / 8 * 8;
+  if (RA > 256) return false;
+  return pair_layout(s1.C, s1.J, RA).stages >= 2;
+}
+
+template <int C>
+static int launch_pair(const __nv_bfloat16* S, const __nv_bfloat16* W1, const __nv_bfloat16* W2, const float* bias1,
+                       const ConvGemmShape& s1, const Epilogue& e2, cudaStream_t st, int sm_count) {
+  const int J = s1.J, RA = (128 + (J - 1) * s1.dil + 7) / 8 * 8, MO = 128 - (J - 1);
+  const PairLayout lay = pair_layout(C, J, RA);
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  DC_CUDA(cudaGetDevice(&dev));
+  if (!(attr_dev_mask & (1 << dev))) {
+    DC_CUDA(cudaFuncSetAttribute(conv_ws_pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_dev_mask |= 1 << dev;
+  }
+  const int tiles_per_clip = (s1.T + MO - 1) / MO;
+  const long long total = (long long)s1.B * tiles_per_clip;
+  DC_CHECK(total > 0 && total < (1ll << 31), DC_ERR_SHAPE, "conv_ws_pair: bad tile count");
+  CUtensorMap tmA, tmW1, tmW2;
+  {
+    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)s1.T, (uint64_t)s1.B};
+    const uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)s1.T * C * 2};
+    const uint32_t box[3] = {(uint32_t)C, (uint32_t)RA, 1};
+    DC_TRY(make_tmap_bf16(&tmA, S, 3, dims, strides, box, C * 2));
+  }
+  for (int w = 0; w < 2; ++w) {
+    const uint64_t K = (uint64_t)J * C;
+    const uint64_t dims[2] = {K, (uint64_t)C};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {(uint32_t)C, (uint32_t)C};
+    DC_TRY(make_tmap_bf16(w ? &tmW2 : &tmW1, w ? W2 : W1, 2, dims, strides, box, C * 2));
+  }
+  const int grid = (int)(total < sm_count ? total : sm_count);
+  const int p1 = s1.dil * (J - 1) / 2, p2 = (J - 1) / 2;
+  {
+    const double rows = (double)s1.B * s1.T;
+    const double macs = 2.0 * rows * C * J * C;
+    const int esig = (e2.res ? 4 : 0) | (e2.add1 ? 8 : 0) | (e2.out0 ? (e2.out0_dt == DT_F32 ? 16 : 32) : 0) | (e2.out1 ? 32 : 0);
+    const double out_bytes = (e2.out0 ? (e2.out0_dt == DT_F32 ? 4.0 : 2.0) : 0.0) + (e2.out1 ? 2.0 : 0.0) +
+                             (e2.res ? 4.0 : 0.0) + (e2.add1 ? 8.0 : 0.0);
+    ProfScope ps(PC_CONV_WS, 2.0 * macs, rows * C * 2.0 + 2.0 * J * C * C * 2.0 + rows * C * out_bytes, st,
+                 "_pair<%d>|C%d N%d J%d d%d e%d", C, C, C, J, s1.dil, esig);
+    conv_ws_pair_kernel<C><<<grid, kPairThreads, lay.total, st>>>(tmA, tmW1, tmW2, s1.T, J, s1.dil, -(p1 + p2), bias1, e2,
+                                                                  epilogue_variant(e2), lay, tiles_per_clip, (int)total);
+  }
+  ++g_launches_ws;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+int launch_conv_ws_pair(const __nv_bfloat16* S, const __nv_bfloat16* W1, const __nv_bfloat16* W2, const float* bias1,
+                        const ConvGemmShape& s1, const ConvGemmShape& s2, const Epilogue& e2, cudaStream_t st,
+                        int sm_count) {
+  DC_CHECK(conv_ws_pair_supported(s1, s2), DC_ERR_SHAPE, "conv_ws_pair: unsupported shapes");
+  DC_CHECK(bias1 != nullptr, DC_ERR_ARG, "conv_ws_pair: conv1 bias missing");
+  if (s1.C == 64) return launch_pair<64>(S, W1, W2, bias1, s1, e2, st, sm_count);
+  return launch_pair<32>(S, W1, W2, bias1, s1, e2, st, sm_count);
 }
 
 bool conv_ws_supported(const ConvGemmShape& s) {

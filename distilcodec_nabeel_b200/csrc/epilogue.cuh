@@ -208,7 +208,8 @@ __device__ __forceinline__ void epilogue_dispatch(const Epilogue& ep, int varian
 // tmem_acc: TMEM address (lane 0) of the tile's accumulator; stg: this warp's 32 x CW fp32 transpose buffer.
 template <int BN, int CW = (BN >= 64 ? 32 : 16) /* chunk width in columns */>
 __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int variant, float* stg, uint32_t tmem_acc, int clip,
-                                              int t0, int n0, int T, int warp, int lane) {
+                                              int t0, int n0, int T, int warp, int lane, int t_lim = 0x7fffffff) {
+  // t_lim: rows t >= min(T, t_lim) are not stored (tiles whose last accumulator rows are not valid outputs)
   constexpr int CPR = CW / 4;             // 16-byte column groups per row (8 or 4)
   constexpr int RPI = 32 / CPR;           // rows covered by one warp-wide access (4 or 8)
   const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -233,7 +234,7 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int variant, f
           make_uint4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
     __syncwarp();
     const int tb = t0 + q * 32 + rsub;  // first row of this lane
-    const int nvalid = min(32 / RPI, max(0, (T - tb + RPI - 1) / RPI));
+    const int nvalid = min(32 / RPI, max(0, (min(T, t_lim) - tb + RPI - 1) / RPI));
     const size_t off0 = ((size_t)clip * T + tb) * (size_t)ep.ldo + n;
     epilogue_dispatch<CW, false>(ep, variant, stg, lane, off0, nvalid, n, b4, g4);
     __syncwarp();

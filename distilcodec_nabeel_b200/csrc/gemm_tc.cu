@@ -145,7 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (ptx::elect_one()) {  // one lane, known to the compiler: operands go to uniform registers
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -167,7 +167,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    if (ptx::elect_one()) {  // one lane, known to the compiler: operands go to uniform registers
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;

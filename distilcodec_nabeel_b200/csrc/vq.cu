@@ -272,7 +272,7 @@ vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (ptx::elect_one()) {  // one lane, known to the compiler: operands go to uniform registers
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -292,7 +292,7 @@ vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (ptx::elect_one()) {  // one lane, known to the compiler: operands go to uniform registers
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {

@@ -75,7 +75,8 @@ int dc_create(int device, int mode, const dc_config* cfg, dc_handle* out);
 int dc_destroy(dc_handle h);
 /* Tunables: "vq_window" (fraction of the rigorous bf16 error bound used as the candidate window, default 0.25;
  * 1.0 = rigorous), "vq_tensor_core" (1 = tcgen05 scorer [default], 0 = CUDA-core scorer), "vq_x2_exact"
- * (0 [default] = ||x||^2 summed in the order of the reference's CPU path, ATen cascade_sum; 1 = correctly rounded). */
+ * (0 [default] = ||x||^2 summed in the order of the reference's CPU path, ATen cascade_sum; 1 = correctly rounded),
+ * "fuse_pairs" (1 [default] = the narrow decoder stages run each conv1 -> SiLU -> conv2 step as one kernel). */
 int dc_set_option(dc_handle h, const char* key, double value);
 
 /* Weight ingestion.  Replaces `load_state_dict` on the three modules (distil_codec.py:91-94): call once per
