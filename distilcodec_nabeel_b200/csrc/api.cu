@@ -151,6 +151,7 @@ struct dc_handle_s {
   bool vq_tc = true;
   bool vq_x2_exact = false;
   bool fuse_pairs = true;
+  int epi_prefetch = 1;
 
   // encoder
   Dense stem;
@@ -327,6 +328,7 @@ static int run_dense(const dc_handle_s* h, const Dense& d, const void* A, int B,
   ConvGemmShape s{B, T, d.C, d.J, d.shift0, d.dil, d.N, d.alg_scale, d.phase_cols, d.zero_taps};
   if (!ep.bias) ep.bias = d.bias;
   ep.ldo = d.N;
+  ep.prefetch = h->epi_prefetch;
   if (h->mode == DC_MODE_BF16)
     return launch_gemm_tc(reinterpret_cast<const __nv_bfloat16*>(A), d.w_bf16, s, ep, st, h->sm_count);
   return launch_gemm_f32(reinterpret_cast<const float*>(A), d.w_f32, s, ep, st);
@@ -341,6 +343,7 @@ static int run_conv_pair(const dc_handle_s* h, const Dense& c1, const Dense& c2,
   if (h->mode == DC_MODE_BF16 && h->fuse_pairs && c1.bias && conv_ws_pair_supported(s1, s2)) {
     if (!e2.bias) e2.bias = c2.bias;
     e2.ldo = c2.N;
+    e2.prefetch = h->epi_prefetch;
     return launch_conv_ws_pair(reinterpret_cast<const __nv_bfloat16*>(S), c1.w_bf16, c2.w_bf16, c1.bias, s1, s2, e2, st,
                                h->sm_count);
   }
@@ -686,6 +689,8 @@ int dc_set_option(dc_handle h, const char* key, double value) {
     h->vq_x2_exact = value != 0.0;
   } else if (!strcmp(key, "fuse_pairs")) {
     h->fuse_pairs = value != 0.0;
+  } else if (!strcmp(key, "epi_prefetch")) {
+    h->epi_prefetch = (int)value;
   } else {
     set_error("unknown option '%s'", key);
     return DC_ERR_ARG;

@@ -67,6 +67,7 @@ struct Epilogue {
   int ldo = 0;
   float scale = 1.f;
   int out1_silu = 1;
+  int prefetch = 1;  // L2-prefetch res / add1 / add2 of the next tile while waiting for its MMAs
 };
 
 // Packed fp32 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, two IEEE fp32 operations per instruction, same rounding as

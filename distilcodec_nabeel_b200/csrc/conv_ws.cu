@@ -163,6 +163,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int clip = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * 128;
       const int as = it % kWsAccStages;
       const uint32_t aphase = (it / kWsAccStages) & 1;
+      epilogue_prefetch(ep, clip, s.T, t0 + (wg & 3) * 32, ((wg - 2) >> 2) * (N / 2), N / 2, lane);
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
       epilogue_tile<N>(ep, variant, stg, tmem_base + as * N, clip, t0, 0, s.T, wg, lane);
@@ -418,6 +419,7 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if ((i & 1) != group) continue;           // group g owns accumulator D2[g]
       const int clip = tile / tiles_per_clip, o0 = (tile % tiles_per_clip) * MO;
       const int b = i & 1;
+      epilogue_prefetch(ep, clip, T, o0 + (wg & 3) * 32, ((wg - 2) >> 2) * (C / 2), C / 2, lane, o0 + MO);
       ptx::mbar_wait(&d2full[b], (i >> 1) & 1);
       ptx::tc_fence_after();
       epilogue_tile<C, 16>(ep, variant, stg, tm_d2 + b * C, clip, o0, 0, T, wg, lane, o0 + MO);

@@ -208,6 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int clip = m_blk / tiles_per_clip, t0 = (m_blk % tiles_per_clip) * 128, n0 = n_blk * BN;
       const int as = it % ACC;
       const uint32_t aphase = (it / ACC) & 1;
+      epilogue_prefetch(ep, clip, s.T, t0 + (wg & 3) * 32, n0 + ((wg - 2) >> 2) * (BN / 2), BN / 2, lane);
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
       epilogue_tile<BN, L::CW>(ep, variant, stg, tmem_base + as * BN, clip, t0, n0, s.T, wg, lane);
@@ -273,8 +274,11 @@ static int launch_cfg(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
                              (e.res ? 4.0 : 0.0) + (e.add1 ? 8.0 : 0.0);
     ProfScope ps(PC_GEMM_TC, 2.0 * macs, rows * s.C * 2.0 + (double)s.N * s.J * s.C * 2.0 + rows * s.N * out_bytes, st,
                  "<%d,%d,%d,%d,%d>|C%d N%d J%d d%d e%d", BN, BK, STAGES, EG, ACC, s.C, s.N, s.J, s.dil, esig);
+    Epilogue eg = e;
+    eg.prefetch = 0;  // A/B on one B200: the L2 prefetch helps the HBM-bound narrow kernels (conv_ws/_pair/_ts,
+                      // -5 %) but costs the tensor-bound wide ones 3 % (extra L2 traffic next to 17 TB/s of operands)
     gemm_tc_kernel<BN, BK, STAGES, EG, ACC><<<grid, L::THREADS, L::TOTAL, st>>>(
-        tmA, tmB, s, e, epilogue_variant(e), tiles_per_clip, (int)m_tiles, n_tiles);
+        tmA, tmB, s, eg, epilogue_variant(e), tiles_per_clip, (int)m_tiles, n_tiles);
   }
   ++g_launches_tc;
   DC_CUDA(cudaGetLastError());
