@@ -1,15 +1,16 @@
-// tcgen05 / TMEM / TMA shifted-row implicit GEMM (DC_MODE_BF16) — the kernel every dense layer of the hot path
-// runs on: pwconv1/2 and 1x1 convs (J = 1), the stem k7, conv_pre k13, the dilated ResBlock convs (J = k taps,
-// tap j = the same TMA box shifted by shift0 + j*dil frames; TMA out-of-bounds zero fill IS the conv's zero
-// padding) and ConvTranspose1d (stride phases stacked along N, union of input shifts along J).
+// tcgen05 / TMEM / TMA shifted-row implicit GEMM (DC_MODE_BF16) — the generic kernel of the hot path's dense layers:
+// pwconv1/2 and 1x1 convs (J = 1), the stem k7, conv_pre k13, the wide dilated ResBlock convs (J = k taps, tap j = the
+// same TMA box shifted by shift0 + j*dil frames; TMA out-of-bounds zero fill IS the conv's zero padding) and
+// ConvTranspose1d (stride phases stacked along N, union of input shifts along J, all-zero taps of a phase skipped).
+// The narrow decoder stages are dispatched to conv_ts.cu (C = N = 128) and conv_ws.cu (C <= 64) from here.
 //
 //   out[b,t,n] = epi( sum_{j<J} sum_{c<C} A[b, t + shift0 + j*dil, c] * W[n, j*C + c] )
 //
-// Persistent, warp-specialised, one CTA per SM (320 threads):
-//   warp 0      TMA producer   : 3-D box (BK channels x 128 frames x 1 clip) of A + 2-D box (BK x BN) of W per stage
-//   warp 1      MMA issuer     : one thread issues tcgen05.mma (M=128, N=BN, K=16) BK/16 times per stage; owns TMEM
-//   warps 2..9  epilogue       : tcgen05.ld 32x32b -> registers -> bias/act/gamma/residual/mean3 -> global
-// Two TMEM accumulators (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Persistent, warp-specialised, one CTA per SM (64 + EG * 256 threads):
+//   warp 0      TMA producer : 3-D box (BK channels x 128 frames x 1 clip) of A + 2-D box (BK x BN) of W per stage
+//   warp 1      MMA issuer   : one elected thread issues tcgen05.mma (M=128, N=BN, K=16) BK/16 times per stage
+//   warps 2..   epilogue     : EG groups of 8 warps (epilogue.cuh): tcgen05.ld -> smem transpose -> fused epilogue
+// ACC TMEM accumulators (ACC x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Tiles are ordered n-fastest so the CTAs running at any moment share a few A row-blocks (read from HBM once) and
 // all of W (<= 27 MB, L2 resident).
 #include "common.cuh"

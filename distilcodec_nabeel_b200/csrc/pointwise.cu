@@ -295,13 +295,9 @@ static int dwconv_ln_dispatch(const float* in, const float* dw_w, const float* d
   constexpr int C = VPL * 128;
   ProfScope ps(dw_w ? PC_DWCONV_LN : PC_LAYERNORM, 0, (double)rows * C * (4.0 + (out_dt == DT_F32 ? 4.0 : 2.0)), st,
                "C%d", C);
-  if (dw_w) {
-    if (out_dt == DT_F32) dwconv_ln_kernel<VPL, true, float><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (float*)out, B, T);
-    else dwconv_ln_kernel<VPL, true, __nv_bfloat16><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (__nv_bfloat16*)out, B, T);
-  } else {
-    if (out_dt == DT_F32) dwconv_ln_kernel<VPL, false, float><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (float*)out, B, T);
-    else dwconv_ln_kernel<VPL, false, __nv_bfloat16><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (__nv_bfloat16*)out, B, T);
-  }
+  // LayerNorm only (the stem / inter-stage / final norms); depthwise conv + LN goes to dwconv_ln_run_kernel
+  if (out_dt == DT_F32) dwconv_ln_kernel<VPL, false, float><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (float*)out, B, T);
+  else dwconv_ln_kernel<VPL, false, __nv_bfloat16><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (__nv_bfloat16*)out, B, T);
   ++g_launches_pw;
   DC_CUDA(cudaGetLastError());
   return DC_OK;

@@ -169,6 +169,27 @@ class Pipeline:
         self._run_host(mel_host, False, codes_out, None)
         return codes_out
 
+    def tokenize_wav(self, wav_host: torch.Tensor, codes_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """wav -> codes entirely on the device (DistilCodec.encode with raw_audio=True, distil_codec.py:545-573 +
+        :99-145) from HOST audio (B, n) fp32 at the model rate, equal lengths: left-pad by one zero sample (:134), GPU
+        log-mel (the reference runs this stage on the CPU), encoder, VQ.  Needs the engine's mel buffers."""
+        B, n = wav_host.shape
+        T = (n + 1 - 256) // 256 + 1
+        if codes_out is None:
+            codes_out = torch.empty(B, T, dtype=torch.int64, pin_memory=True)
+        step = self._chunk(B, T)
+        with torch.cuda.device(self.dev):
+            for b0 in range(0, B, step):
+                b1 = min(B, b0 + step)
+                w = wav_host[b0:b1].to(self.dev, non_blocking=True)
+                self.h2d_bytes += w.numel() * 4
+                mel = self.eng.mel(torch.nn.functional.pad(w, (1, 0)).contiguous())
+                codes, _ = self.encode_device(mel)
+                codes_out[b0:b1].copy_(codes, non_blocking=True)
+                self.d2h_bytes += codes.numel() * 8
+            torch.cuda.current_stream(self.dev).synchronize()
+        return codes_out
+
     def decode(self, codes_host: torch.Tensor, wav_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """codes->wav leg (decode_from_codes, distil_codec.py:581-594) from HOST codes (B,T) int64."""
         B, T = codes_host.shape

@@ -192,3 +192,22 @@ def test_tiny_clips_all_stages(T, mode):
     wav = eng.generator(quant)
     ref = R.generator_forward(sd, quant.transpose(1, 2).cpu())[:, 0]
     assert wav.shape == (2, 256 * T) and rel_err(wav, ref) < TOL[mode]
+
+
+def test_non_default_stream_and_wav_tokenisation():
+    """All work is enqueued on the caller's current stream (C-ABI contract); wav -> codes on the device (GPU mel)."""
+    from distilcodec_nabeel_b200.sharding import Pipeline
+    from tests.golden.inputs import make_wav
+    eng = engine("W1", "bf16")
+    mel = make_mel(2, 50, seed=61).to(eng.device)
+    ref_codes, ref_wav = Pipeline(eng).reconstruct_device(mel)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(eng.device)
+    with torch.cuda.stream(side):
+        codes, wav = Pipeline(eng).reconstruct_device(mel)
+    side.synchronize()
+    assert torch.equal(codes, ref_codes) and torch.equal(wav, ref_wav)
+    wavs = make_wav(3, 256 * 40 + 100, seed=62)
+    c_all = Pipeline(eng).tokenize_wav(wavs.pin_memory())
+    c_one = torch.cat([Pipeline(eng).tokenize_wav(wavs[i:i + 1].pin_memory()) for i in range(3)])
+    assert c_all.shape == (3, 40) and torch.equal(c_all, c_one)       # batch-independent
