@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdistilcodec_b200.so")
+LIB_PATH = os.environ.get("DC_LIB") or os.path.join(HERE, "libdistilcodec_b200.so")  # DC_LIB: experiment builds
 
 DC_OK = 0
 MODE_FP32, MODE_BF16 = 0, 1

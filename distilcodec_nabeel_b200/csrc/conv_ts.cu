@@ -159,7 +159,7 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // this warp's region: 32 channels (one 128-byte line per row) x 64 rows
       epilogue_prefetch(ep, clip, s.T, t0 + (warp16 >> 2) * 64, (warp16 & 3) * 32, 32, lane);
       epilogue_prefetch(ep, clip, s.T, t0 + (warp16 >> 2) * 64 + 32, (warp16 & 3) * 32, 32, lane);
-      ptx::mbar_wait(&tfull[p], (it >> 1) & 1);
+      ptx::mbar_wait_sleepy(&tfull[p], (it >> 1) & 1);
       ptx::tc_fence_after();
       epilogue_tile_transposed(ep, variant, stg, tmem_base + p * 256, clip, t0, s.T, warp16, lane);
       ptx::tc_fence_before();

@@ -164,7 +164,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int as = it % kWsAccStages;
       const uint32_t aphase = (it / kWsAccStages) & 1;
       epilogue_prefetch(ep, clip, s.T, t0 + (wg & 3) * 32, ((wg - 2) >> 2) * (N / 2), N / 2, lane);
-      ptx::mbar_wait(&tfull[as], aphase);
+      ptx::mbar_wait_sleepy(&tfull[as], aphase);
       ptx::tc_fence_after();
       epilogue_tile<N>(ep, variant, stg, tmem_base + as * N, clip, t0, 0, s.T, wg, lane);
       ptx::tc_fence_before();
@@ -374,7 +374,7 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int b = i & 1;
       const int gt = o0 - p2 + row;                      // sequence position of this t row
       const bool inside = gt >= 0 && gt < T;
-      ptx::mbar_wait(&d1full[b], (i >> 1) & 1);
+      ptx::mbar_wait_sleepy(&d1full[b], (i >> 1) & 1);
       ptx::tc_fence_after();
       ptx::mbar_wait(&tempty[b], ((i >> 1) & 1) ^ 1);    // conv2 of tile i-2 has finished reading this t buffer
       uint8_t* trow = sT + b * lay.t_bytes + row * PITCH;
@@ -420,7 +420,7 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int clip = tile / tiles_per_clip, o0 = (tile % tiles_per_clip) * MO;
       const int b = i & 1;
       epilogue_prefetch(ep, clip, T, o0 + (wg & 3) * 32, ((wg - 2) >> 2) * (C / 2), C / 2, lane, o0 + MO);
-      ptx::mbar_wait(&d2full[b], (i >> 1) & 1);
+      ptx::mbar_wait_sleepy(&d2full[b], (i >> 1) & 1);
       ptx::tc_fence_after();
       epilogue_tile<C, 16>(ep, variant, stg, tm_d2 + b * C, clip, o0, 0, T, wg, lane, o0 + MO);
       ptx::tc_fence_before();

@@ -210,7 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int as = it % ACC;
       const uint32_t aphase = (it / ACC) & 1;
       epilogue_prefetch(ep, clip, s.T, t0 + (wg & 3) * 32, n0 + ((wg - 2) >> 2) * (BN / 2), BN / 2, lane);
-      ptx::mbar_wait(&tfull[as], aphase);
+      ptx::mbar_wait_sleepy(&tfull[as], aphase);
       ptx::tc_fence_after();
       epilogue_tile<BN, L::CW>(ep, variant, stg, tmem_base + as * BN, clip, t0, n0, s.T, wg, lane);
       ptx::tc_fence_before();

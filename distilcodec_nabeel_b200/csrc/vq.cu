@@ -341,7 +341,7 @@ vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       float best = INFINITY;
       int cnt = 0;
       for (int t = t_begin; t < t_end; ++t) {
-        ptx::mbar_wait(tfull, tphase);
+        ptx::mbar_wait_sleepy(tfull, tphase);
         tphase ^= 1;
         ptx::tc_fence_after();
         const int n0 = t * VQ_BN;
