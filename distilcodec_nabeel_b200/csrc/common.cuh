@@ -148,6 +148,10 @@ bool conv_ts_supported(const ConvGemmShape& s);
 int launch_conv_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
                    cudaStream_t st, int sm_count);
 uint64_t conv_ts_launch_count();
+// tap-shared variant for the wide convs (C >= 256, N % 256 == 0, J > 1)
+bool conv_tsw_supported(const ConvGemmShape& s);
+int launch_conv_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
+                    cudaStream_t st, int sm_count);
 
 // pointwise / bandwidth-bound kernels (pointwise.cu)
 int launch_transpose_ncl_to_nlc(const float* in, void* out, int out_dt, int B, int C, int T, cudaStream_t st);

@@ -176,6 +176,225 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ================================================================================================ wide variant
+// Tap-shared activations for the WIDE decoder convs (C = 256 / 512, N a multiple of 256, J > 1): the generic kernel
+// (gemm_tc.cu) re-reads the same 128 activation rows from L2 once per tap; here one TMA box per 64-channel chunk
+// brings 128 + (J-1)*dil rows and all J taps read it through row-shifted descriptors, so the L2 -> SM operand
+// traffic of a k = 11 conv drops 29 % (528 -> 375 KB per tile and chunk).  128 x 256 tiles, two TMEM accumulators,
+// weights stream through a 4-stage ring of 32 KB (tap, chunk) tiles, activations through 2 chunk buffers.
+namespace tsw {
+constexpr int BN = 256, BK = 64;
+constexpr int A_ROWS = 184;                       // 128 + max halo (50), multiple of 8
+constexpr int A_BYTES = A_ROWS * BK * 2;          // 23,552 B (23 x 1024) per chunk buffer
+constexpr int A_STAGES = 2;
+constexpr int B_BYTES = BN * BK * 2;              // 32 KB per (tap, chunk) weight tile
+constexpr int B_STAGES = 4;
+constexpr int A_OFF = 0, B_OFF = A_STAGES * A_BYTES, STG_OFF = B_OFF + B_STAGES * B_BYTES;
+constexpr int STG_BYTES_1 = 8 * 32 * 32 * 4;      // EG = 1: 32-column chunks
+constexpr int STG_BYTES_2 = 16 * 32 * 16 * 4;     // EG = 2: 16-column chunks
+constexpr int BAR_OFF = STG_OFF + 32768;
+constexpr int TOTAL = BAR_OFF + 256 + 1024;
+static_assert(STG_BYTES_1 == 32768 && STG_BYTES_2 == 32768 && TOTAL <= 232448, "shared memory budget");
+}  // namespace tsw
+
+template <int EG>
+__global__ void __launch_bounds__(64 + EG * 256, 1)
+conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvGemmShape s,
+                Epilogue ep, int variant, int tiles_per_clip, int m_tiles, int n_tiles) {
+  using namespace tsw;
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, BN);
+  constexpr int CW = EG == 2 ? 16 : 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem + A_OFF;
+  uint8_t* sB = smem + B_OFF;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem + BAR_OFF);  // [A_STAGES]
+  uint64_t* aempty = afull + A_STAGES;
+  uint64_t* bfull = aempty + A_STAGES;                             // [B_STAGES]
+  uint64_t* bempty = bfull + B_STAGES;
+  uint64_t* tfull = bempty + B_STAGES;                             // [2]
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int kchunks = s.C / BK;
+  const int total_tiles = m_tiles * n_tiles;
+  const uint32_t a_bytes = (uint32_t)(((128 + (s.J - 1) * s.dil + 7) / 8 * 8) * BK * 2);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < A_STAGES; ++i) {
+        ptx::mbar_init(&afull[i], 1);
+        ptx::mbar_init(&aempty[i], 1);
+      }
+      for (int i = 0; i < B_STAGES; ++i) {
+        ptx::mbar_init(&bfull[i], 1);
+        ptx::mbar_init(&bempty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&tfull[i], 1);
+        ptx::mbar_init(&tempty[i], 8);
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<512>(tmem_slot);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      int as = 0, bs = 0;
+      uint32_t aphase = 0, bphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n0 = (tile % n_tiles) * BN;
+        const int clip = m_blk / tiles_per_clip, t0 = (m_blk % tiles_per_clip) * 128;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          ptx::mbar_wait(&aempty[as], aphase ^ 1);
+          ptx::mbar_expect_tx(&afull[as], a_bytes);
+          ptx::tma_load_3d(sA + as * A_BYTES, &tmA, &afull[as], kc * BK, t0 + s.shift0, clip);
+          if (++as == A_STAGES) { as = 0; aphase ^= 1; }
+          for (int j = 0; j < s.J; ++j) {
+            ptx::mbar_wait(&bempty[bs], bphase ^ 1);
+            ptx::mbar_expect_tx(&bfull[bs], B_BYTES);
+            ptx::tma_load_2d(sB + bs * B_BYTES, &tmW, &bfull[bs], j * s.C + kc * BK, n0);
+            if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (ptx::elect_one()) {
+      int as = 0, bs = 0, it = 0;
+      uint32_t aphase = 0, bphase = 0;
+      const uint32_t tap_step = (uint32_t)(s.dil * BK * 2) >> 4;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int p = it & 1;
+        ptx::mbar_wait(&tempty[p], ((it >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d0 = tmem_base + p * BN;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          ptx::mbar_wait(&afull[as], aphase);
+          ptx::tc_fence_after();
+          uint64_t da = ptx::make_smem_desc<128>(ptx::smem_u32(sA + as * A_BYTES));
+          for (int j = 0; j < s.J; ++j) {
+            ptx::mbar_wait(&bfull[bs], bphase);
+            ptx::tc_fence_after();
+            const uint64_t db = ptx::make_smem_desc<128>(ptx::smem_u32(sB + bs * B_BYTES));
+            const uint32_t acc = (kc | j) != 0 ? 1u : 0u;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) ptx::mma_bf16_ss(d0, da + 2 * k, db + 2 * k, IDESC, acc | (uint32_t)(k != 0));
+            ptx::mma_commit(&bempty[bs]);
+            if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
+            da += tap_step;
+          }
+          ptx::mma_commit(&aempty[as]);
+          if (++as == A_STAGES) { as = 0; aphase ^= 1; }
+        }
+        ptx::mma_commit(&tfull[p]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: EG groups of 8 warps on alternate tiles
+    float* stg = reinterpret_cast<float*>(smem + STG_OFF) + (warp - 2) * (32 * CW);
+    const int group = (warp - 2) >> 3;
+    const int wg = 2 + ((warp - 2) & 7);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      if (EG > 1 && (it & 1) != group) continue;
+      const int m_blk = tile / n_tiles, n0 = (tile % n_tiles) * BN;
+      const int clip = m_blk / tiles_per_clip, t0 = (m_blk % tiles_per_clip) * 128;
+      const int p = it & 1;
+      ptx::mbar_wait_sleepy(&tfull[p], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      epilogue_tile<BN, CW>(ep, variant, stg, tmem_base + p * BN, clip, t0, n0, s.T, wg, lane);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[p]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+bool conv_tsw_supported(const ConvGemmShape& s) {
+  return s.J > 1 && s.C % tsw::BK == 0 && s.C >= 256 && s.N % tsw::BN == 0 && s.zero_taps == 0 &&
+         128 + (s.J - 1) * s.dil <= tsw::A_ROWS;
+}
+
+template <int EG>
+static int launch_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
+                      cudaStream_t st, int sm_count) {
+  using namespace tsw;
+  static int attr_dev_mask = 0;
+  int dev = 0;
+  DC_CUDA(cudaGetDevice(&dev));
+  if (!(attr_dev_mask & (1 << dev))) {
+    DC_CUDA(cudaFuncSetAttribute(conv_tsw_kernel<EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
+    attr_dev_mask |= 1 << dev;
+  }
+  const int tiles_per_clip = (s.T + 127) / 128;
+  const long long m_tiles = (long long)s.B * tiles_per_clip;
+  const int n_tiles = s.N / BN;
+  DC_CHECK(m_tiles * n_tiles > 0 && m_tiles * n_tiles < (1ll << 31), DC_ERR_SHAPE, "conv_tsw: bad tile count");
+  const int RA = (128 + (s.J - 1) * s.dil + 7) / 8 * 8;
+  CUtensorMap tmA, tmW;
+  {
+    const uint64_t dims[3] = {(uint64_t)s.C, (uint64_t)s.T, (uint64_t)s.B};
+    const uint64_t strides[2] = {(uint64_t)s.C * 2, (uint64_t)s.T * s.C * 2};
+    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)RA, 1};
+    DC_TRY(make_tmap_bf16(&tmA, A, 3, dims, strides, box, 128));
+  }
+  {
+    const uint64_t K = (uint64_t)s.J * s.C;
+    const uint64_t dims[2] = {K, (uint64_t)s.N};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    DC_TRY(make_tmap_bf16(&tmW, W, 2, dims, strides, box, 128));
+  }
+  const long long total = m_tiles * n_tiles;
+  const int grid = (int)(total < sm_count ? total : sm_count);
+  {
+    const double rows = (double)s.B * s.T;
+    const double macs = rows * s.N * s.J * s.C * s.alg_scale;
+    const int esig = (e.act ? 1 : 0) | (e.gamma ? 2 : 0) | (e.res ? 4 : 0) | (e.add1 ? 8 : 0) |
+                     (e.out0 ? (e.out0_dt == DT_F32 ? 16 : 32) : 0) | (e.out1 ? 32 : 0);
+    const double out_bytes = (e.out0 ? (e.out0_dt == DT_F32 ? 4.0 : 2.0) : 0.0) + (e.out1 ? 2.0 : 0.0) +
+                             (e.res ? 4.0 : 0.0) + (e.add1 ? 8.0 : 0.0);
+    ProfScope ps(PC_CONV_TS, 2.0 * macs, rows * s.C * 2.0 + (double)s.N * s.J * s.C * 2.0 + rows * s.N * out_bytes, st,
+                 "w<%d>|C%d N%d J%d d%d e%d", EG, s.C, s.N, s.J, s.dil, esig);
+    Epilogue eg = e;
+    eg.prefetch = 0;
+    conv_tsw_kernel<EG><<<grid, 64 + EG * 256, TOTAL, st>>>(tmA, tmW, s, eg, epilogue_variant(e), tiles_per_clip,
+                                                            (int)m_tiles, n_tiles);
+  }
+  ++g_launches_ts;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
+int launch_conv_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
+                    cudaStream_t st, int sm_count) {
+  DC_CHECK(conv_tsw_supported(s), DC_ERR_SHAPE, "conv_tsw: unsupported shape");
+  if (e.res || (e.out0 && e.out1)) return launch_tsw<2>(A, W, s, e, st, sm_count);
+  return launch_tsw<1>(A, W, s, e, st, sm_count);
+}
+
 bool conv_ts_supported(const ConvGemmShape& s) {
   return s.C == ts::C && s.N == ts::N && 256 + (s.J - 1) * s.dil <= ts::A_ROWS && s.J >= 1;
 }
