@@ -188,22 +188,28 @@ constexpr int A_ROWS = 184;                       // 128 + max halo (50), multip
 constexpr int A_BYTES = A_ROWS * BK * 2;          // 23,552 B (23 x 1024) per chunk buffer
 constexpr int A_STAGES = 2;
 constexpr int B_BYTES = BN * BK * 2;              // 32 KB per (tap, chunk) weight tile
-constexpr int B_STAGES = 4;
-constexpr int A_OFF = 0, B_OFF = A_STAGES * A_BYTES, STG_OFF = B_OFF + B_STAGES * B_BYTES;
-constexpr int STG_BYTES_1 = 8 * 32 * 32 * 4;      // EG = 1: 32-column chunks
-constexpr int STG_BYTES_2 = 16 * 32 * 16 * 4;     // EG = 2: 16-column chunks
-constexpr int BAR_OFF = STG_OFF + 32768;
-constexpr int TOTAL = BAR_OFF + 256 + 1024;
-static_assert(STG_BYTES_1 == 32768 && STG_BYTES_2 == 32768 && TOTAL <= 232448, "shared memory budget");
+constexpr int A_OFF = 0, B_OFF = A_STAGES * A_BYTES;
+// <EG, CW, BST>: epilogue groups, transpose chunk width, weight ring depth.  <1,32,4> conv1-type epilogues;
+// <2,16,4> residual epilogues with long K; <2,32,3> residual epilogues with short K (epilogue-bound: wider chunks
+// matter more than the 4th weight stage)
+template <int EG, int CW, int BST>
+struct Cfg {
+  static constexpr int STG_OFF = B_OFF + BST * B_BYTES;
+  static constexpr int STG_BYTES = EG * 8 * 32 * CW * 4;
+  static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static_assert(TOTAL <= 232448, "shared memory budget");
+};
 }  // namespace tsw
 
-template <int EG>
+template <int EG, int CW, int BST>
 __global__ void __launch_bounds__(64 + EG * 256, 1)
 conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvGemmShape s,
                 Epilogue ep, int variant, int tiles_per_clip, int m_tiles, int n_tiles) {
   using namespace tsw;
+  using L = Cfg<EG, CW, BST>;
+  constexpr int B_STAGES = BST, STG_OFF = L::STG_OFF, BAR_OFF = L::BAR_OFF;
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, BN);
-  constexpr int CW = EG == 2 ? 16 : 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem + A_OFF;
@@ -337,15 +343,16 @@ bool conv_tsw_supported(const ConvGemmShape& s) {
          128 + (s.J - 1) * s.dil <= tsw::A_ROWS;
 }
 
-template <int EG>
+template <int EG, int CW, int BST>
 static int launch_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
                       cudaStream_t st, int sm_count) {
   using namespace tsw;
+  constexpr int TOTAL = Cfg<EG, CW, BST>::TOTAL;
   static int attr_dev_mask = 0;
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
   if (!(attr_dev_mask & (1 << dev))) {
-    DC_CUDA(cudaFuncSetAttribute(conv_tsw_kernel<EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
+    DC_CUDA(cudaFuncSetAttribute(conv_tsw_kernel<EG, CW, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
     attr_dev_mask |= 1 << dev;
   }
   const int tiles_per_clip = (s.T + 127) / 128;
@@ -377,10 +384,10 @@ static int launch_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
     const double out_bytes = (e.out0 ? (e.out0_dt == DT_F32 ? 4.0 : 2.0) : 0.0) + (e.out1 ? 2.0 : 0.0) +
                              (e.res ? 4.0 : 0.0) + (e.add1 ? 8.0 : 0.0);
     ProfScope ps(PC_CONV_TS, 2.0 * macs, rows * s.C * 2.0 + (double)s.N * s.J * s.C * 2.0 + rows * s.N * out_bytes, st,
-                 "w<%d>|C%d N%d J%d d%d e%d", EG, s.C, s.N, s.J, s.dil, esig);
+                 "w<%d,%d,%d>|C%d N%d J%d d%d e%d", EG, CW, BST, s.C, s.N, s.J, s.dil, esig);
     Epilogue eg = e;
     eg.prefetch = 0;
-    conv_tsw_kernel<EG><<<grid, 64 + EG * 256, TOTAL, st>>>(tmA, tmW, s, eg, epilogue_variant(e), tiles_per_clip,
+    conv_tsw_kernel<EG, CW, BST><<<grid, 64 + EG * 256, TOTAL, st>>>(tmA, tmW, s, eg, epilogue_variant(e), tiles_per_clip,
                                                             (int)m_tiles, n_tiles);
   }
   ++g_launches_ts;
@@ -391,8 +398,11 @@ static int launch_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
 int launch_conv_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
                     cudaStream_t st, int sm_count) {
   DC_CHECK(conv_tsw_supported(s), DC_ERR_SHAPE, "conv_tsw: unsupported shape");
-  if (e.res || (e.out0 && e.out1)) return launch_tsw<2>(A, W, s, e, st, sm_count);
-  return launch_tsw<1>(A, W, s, e, st, sm_count);
+  if (e.res || (e.out0 && e.out1)) {
+    if (s.J * s.C <= 1792 && s.N == 256) return launch_tsw<2, 32, 3>(A, W, s, e, st, sm_count);
+    return launch_tsw<2, 16, 4>(A, W, s, e, st, sm_count);
+  }
+  return launch_tsw<1, 32, 4>(A, W, s, e, st, sm_count);
 }
 
 bool conv_ts_supported(const ConvGemmShape& s) {

@@ -299,10 +299,8 @@ int launch_gemm_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGem
   }
   if (conv_ws_supported(s)) return launch_conv_ws(A, W, s, e, st, sm_count);  // narrow decoder stages
   if (conv_ts_supported(s)) return launch_conv_ts(A, W, s, e, st, sm_count);  // C = N = 128 decoder stage
-  // wide convs: tap-shared activations (conv_ts.cu), except short-K layers with a residual epilogue, which are
-  // epilogue-bound and do better with the generic kernel's 32-column transpose chunks (A/B: 5.7 vs 7.5 ms at k = 3)
-  const bool short_k_res = (e.res || (e.out0 && e.out1)) && s.J * s.C <= 1792 && s.N == 256;
-  if (!short_k_res && conv_tsw_supported(s)) return launch_conv_tsw(A, W, s, e, st, sm_count);
+  // wide convs (C >= 256, J > 1): tap-shared activations (conv_ts.cu)
+  if (conv_tsw_supported(s)) return launch_conv_tsw(A, W, s, e, st, sm_count);
   if (s.C % 64 != 0) {
     DC_CHECK(s.N % 32 == 0, DC_ERR_SHAPE, "gemm_tc: unsupported N for C=32");
     if (s.N % 64 == 0) return launch_cfg<64, 32, 8>(A, W, s, e, st, sm_count);
