@@ -336,17 +336,27 @@ static int run_dense(const dc_handle_s* h, const Dense& d, const void* A, int B,
 
 // One ResBlock1 step (convnext_utils.py:109-112): ep2( c2( silu( c1(S) + b1 ) ) ).  In bf16 mode the narrow stages
 // run it as ONE kernel (conv_ws.cu, conv1's output stays in shared memory); otherwise two implicit GEMMs through `tb`.
+static bool pair_fuses(const dc_handle_s* h, const Dense& c1, const Dense& c2, int B, int T) {
+  ConvGemmShape s1{B, T, c1.C, c1.J, c1.shift0, c1.dil, c1.N, c1.alg_scale, c1.phase_cols, c1.zero_taps};
+  ConvGemmShape s2{B, T, c2.C, c2.J, c2.shift0, c2.dil, c2.N, c2.alg_scale, c2.phase_cols, c2.zero_taps};
+  return h->mode == DC_MODE_BF16 && h->fuse_pairs && c1.bias && conv_ws_pair_supported(s1, s2);
+}
+// NOTE on aliasing: the fused kernel reads S with a halo of up to 30 rows per tile while other CTAs write their
+// tiles' outputs, so e2.out1 must NOT alias S there (the caller ping-pongs the bf16 buffers); e2.res may alias
+// e2.out0 (element-wise, no halo).  In the two-kernel form out1 may alias S (conv1 has finished reading it).
 static int run_conv_pair(const dc_handle_s* h, const Dense& c1, const Dense& c2, const void* S, void* tb, int B, int T,
                          Epilogue e2, cudaStream_t st) {
   ConvGemmShape s1{B, T, c1.C, c1.J, c1.shift0, c1.dil, c1.N, c1.alg_scale, c1.phase_cols, c1.zero_taps};
   ConvGemmShape s2{B, T, c2.C, c2.J, c2.shift0, c2.dil, c2.N, c2.alg_scale, c2.phase_cols, c2.zero_taps};
-  if (h->mode == DC_MODE_BF16 && h->fuse_pairs && c1.bias && conv_ws_pair_supported(s1, s2)) {
+  if (pair_fuses(h, c1, c2, B, T)) {
+    DC_CHECK(e2.out1 != S && e2.out0 != S, DC_ERR_ARG, "fused conv pair: an output aliases the activation input");
     if (!e2.bias) e2.bias = c2.bias;
     e2.ldo = c2.N;
     e2.prefetch = h->epi_prefetch;
     return launch_conv_ws_pair(reinterpret_cast<const __nv_bfloat16*>(S), c1.w_bf16, c2.w_bf16, c1.bias, s1, s2, e2, st,
                                h->sm_count);
   }
+  DC_CHECK(S != tb, DC_ERR_ARG, "conv pair: the intermediate buffer aliases the activation input");
   Epilogue e1;  // xt = silu(c1(silu(x)))
   e1.act = ACT_SILU;
   e1.out0 = tb;
@@ -565,10 +575,14 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
           Epilogue e2;  // x = c2(silu(c1(silu(x)))) + x
           e2.res = cur_x;
           e2.res_dt = DT_F32;
+          // bf16 silu(x') for the next step: the fused kernel must not write the buffer it is reading (halo rows
+          // of neighbouring tiles), so it ping-pongs between sb and tb (tb is free there: t never leaves the chip)
+          const bool fused = pair_fuses(h, h->rb[i][b][0][n3], h->rb[i][b][1][n3], B, L);
+          void* s_out = (fused && cur_s == sb) ? tb : sb;
           if (n3 < 2) {
             e2.out0 = X[b];
             e2.out0_dt = DT_F32;
-            e2.out1 = sb;
+            e2.out1 = s_out;
             e2.out1_dt = ad;
           } else if (b < 2) {
             e2.out0 = X[b];
@@ -583,7 +597,7 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
           }
           DC_TRY(run_conv_pair(h, h->rb[i][b][0][n3], h->rb[i][b][1][n3], cur_s, tb, B, L, e2, st));
           cur_x = X[b];
-          cur_s = sb;
+          cur_s = s_out;
         }
       }
     }
