@@ -211,3 +211,19 @@ def test_non_default_stream_and_wav_tokenisation():
     c_all = Pipeline(eng).tokenize_wav(wavs.pin_memory())
     c_one = torch.cat([Pipeline(eng).tokenize_wav(wavs[i:i + 1].pin_memory()) for i in range(3)])
     assert c_all.shape == (3, 40) and torch.equal(c_all, c_one)       # batch-independent
+
+
+def test_large_batch_is_deterministic_and_batch_invariant():
+    """Race / aliasing detector at a size where every persistent CTA processes hundreds of tiles: the same input
+    twice gives bit-identical codes and waveform, and a clip's result does not depend on its batch (a kernel that
+    read activations another CTA had already overwritten would break both)."""
+    eng = engine("W1", "bf16")
+    mel = make_mel(8, 937, seed=123).repeat(8, 1, 1).to(eng.device)             # 64 clips x 10 s
+    from distilcodec_nabeel_b200.sharding import Pipeline
+    pipe = Pipeline(eng)
+    c1, w1 = pipe.reconstruct_device(mel)
+    c2, w2 = pipe.reconstruct_device(mel)
+    assert torch.equal(c1, c2) and torch.equal(w1, w2)
+    assert torch.equal(c1[:8], c1[8:16]) and torch.equal(w1[:8], w1[56:64])   # repeated clips, different tiles/CTAs
+    c3, w3 = pipe.reconstruct_device(mel[:3].contiguous())
+    assert torch.equal(c3, c1[:3]) and torch.equal(w3, w1[:3])
