@@ -1,8 +1,11 @@
 // Bandwidth-bound kernels of the hot path (vectorised, coalesced, one pass over HBM each) and the one-time
 // weight prepack kernels.  All activations are channels-last (rows = frames, C contiguous).
 #include "common.cuh"
+#include "ptx.cuh"
 
 #include <string.h>
+#include <algorithm>
+#include <type_traits>
 
 namespace dc {
 
@@ -151,137 +154,250 @@ __global__ void __launch_bounds__(256) dwconv_ln_kernel(const float* __restrict_
   }
 }
 
-// ---- depthwise k7 + LayerNorm, sliding-window form (the ConvNeXt blocks' kernel) ------------------------------------
-// A block owns RUN consecutive frames of one clip and all C channels; thread i owns channels 4i..4i+3 for the whole
-// run, so its 7 x 4 depthwise weights, bias and LayerNorm affine live in registers and every input row is loaded from
-// global memory exactly ONCE (7-row register window; the warp-per-frame kernel above re-reads each row 7 times
-// through L1, which caps it at ~0.4 of HBM peak).  Rows are processed in batches of R so that R row loads are in
-// flight per thread; LayerNorm statistics are two-pass (mean, then centred sum of squares) across the block's warps
-// through shared memory.  Algorithmic HBM bytes per frame: C*4 read + C*sizeof(TOut) written.
-template <int C, typename TOut>
-__global__ void __launch_bounds__(C / 4) dwconv_ln_run_kernel(const float* __restrict__ in,
-                                                              const float* __restrict__ dw_w /*[7][C]*/,
-                                                              const float* __restrict__ dw_b,
-                                                              const float* __restrict__ ln_w,
-                                                              const float* __restrict__ ln_b, TOut* __restrict__ out,
-                                                              int T, int run) {
-  constexpr int NW = C / 128, R = 8;
-  // prefetching costs 32 registers: at C = 1024 (256 threads) that halves the resident blocks and loses more than
-  // it gains (measured 2.7 vs 3.4 TB/s); below that it wins (C = 768: 3.7 vs 3.1 TB/s)
-  constexpr bool PREFETCH = C <= 768;
-  static_assert(R == 8, "warp_sum8 reduces 8 rows at once");
+// ---- depthwise k7 + LayerNorm, streaming form (the ConvNeXt blocks' kernel) ------------------------------------------
+// Thread i owns channels 4i..4i+3 (its 7 x 4 depthwise weights, bias and LayerNorm affine live in registers) and walks
+// down the frames with a 14-row register window, 8 output rows per batch, so every input row is read from HBM once.
+// Data movement: the grid is persistent (one CTA per resident slot); each CTA takes a contiguous range of
+// (clip, 8-row batch) items.  Clips are back to back in HBM, so the rows it needs form one contiguous range of
+// "chunks" (chunk k of a clip = rows 8k-3 .. 8k+4; flat id = clip * (nbT + 1) + k) that the bulk-copy engine
+// (cp.async.bulk + mbarrier) streams through an NST-deep shared-memory ring, issued by one thread: no load, address
+// or boundary instruction is left in the compute warps' stream, and the ring never drains between clips (no per-run
+// start-up bubble, no tail wave).  Rows outside the clip read as zero (= the conv's zero padding) on a slow path that
+// only boundary batches take.  LayerNorm statistics are two-pass (mean, then centred sum of squares): an 8-row
+// shuffle butterfly per warp, partials through shared memory, lane r of every warp finishes row r and broadcasts.
+// Algorithmic HBM bytes per frame: C*4 read + C*sizeof(TOut) written.  Measured (B200, inside the encoder stage at
+// the power-capped ~1.3 GHz): 4.3-4.8 TB/s = 0.65-0.73 of the copy peak; alone at 1.9 GHz (ncu) 6.0 TB/s = 0.91.
+// History: a warp-per-frame kernel re-reading rows through L1 reached 0.4; register-prefetched global loads 0.60 (a
+// third of its issue slots were load addressing and predicates); a single-sync pairwise-merge (Chan) variant needed
+// 162 registers and was no faster.
+template <int C, typename TOut, int NST, int MINB>
+__global__ void __launch_bounds__(C / 4, MINB) dwconv_ln_stream_kernel(const float* __restrict__ in,
+                                                                        const float* __restrict__ dw_w /*[7][C]*/,
+                                                                        const float* __restrict__ dw_b,
+                                                                        const float* __restrict__ ln_w,
+                                                                        const float* __restrict__ ln_b,
+                                                                        TOut* __restrict__ out, int B, int T) {
+  constexpr int R = 8, NW = C / 128;
+  constexpr uint32_t ROW_BYTES = C * 4, STAGE_BYTES = R * ROW_BYTES;
+  extern __shared__ __align__(128) uint8_t dsm[];
   __shared__ __align__(16) float red[2][R][8];  // [pass][row][warp], padded to 8 warps (unused slots stay 0)
-  for (int i = threadIdx.x; i < 2 * R * 8; i += C / 4) (&red[0][0][0])[i] = 0.f;
-  __syncthreads();
-  const int my_row = ((threadIdx.x >> 4) & 1) * 4 + ((threadIdx.x >> 3) & 1) * 2 + ((threadIdx.x >> 2) & 1);
+  __shared__ __align__(8) uint64_t full[NST];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nbT = (T + R - 1) / R;  // batches per clip; a clip has chunks 0 .. nbT (chunk k = rows 8k-3 .. 8k+4)
+  const long long items = (long long)B * nbT;
+  const long long i0 = items * blockIdx.x / gridDim.x, i1 = items * (blockIdx.x + 1) / gridDim.x;
+  if (i0 >= i1) return;
+  int b = (int)(i0 / nbT), m = (int)(i0 - (long long)b * nbT);
+  const int b_last = (int)((i1 - 1) / nbT), m_last = (int)((i1 - 1) - (long long)b_last * nbT);
+  const int q_last = (int)(((long long)b_last * (nbT + 1) + m_last + 1) - ((long long)b * (nbT + 1) + m));
+  for (int i = tid; i < 2 * R * 8; i += C / 4) (&red[0][0][0])[i] = 0.f;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) ptx::mbar_init(&full[s], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  // producer (thread 0): ring index `issued` <-> chunk (pb, pk) in slot pslot
+  int issued = 0, pb = b, pk = m, pslot = 0;
+  auto issue_upto = [&](int q_hi) {
+    q_hi = min(q_hi, q_last);
+    while (issued <= q_hi) {
+      const int g = R * pk - 3;
+      const int lo = max(0, -g), hi = min(R, T - g);
+      const uint32_t bytes = hi > lo ? (uint32_t)(hi - lo) * ROW_BYTES : 0u;
+      ptx::mbar_expect_tx(&full[pslot], bytes);
+      if (bytes)
+        ptx::bulk_load_1d(dsm + (size_t)pslot * STAGE_BYTES + (size_t)lo * ROW_BYTES,
+                          in + ((size_t)pb * T + (size_t)(g + lo)) * C, bytes, &full[pslot]);
+      ++issued;
+      if (++pslot == NST) pslot = 0;
+      if (++pk > nbT) {
+        pk = 0;
+        ++pb;
+      }
+    }
+  };
+  if (tid == 0) issue_upto(NST - 1);
   const int c = tid * 4;
-  const int t_begin = blockIdx.x * run, t_end = min(T, t_begin + run);
-  const float* ib = in + (size_t)blockIdx.y * T * C + c;
-  TOut* ob = out + (size_t)blockIdx.y * T * C + c;
+  const int my_row = ((tid >> 4) & 1) * 4 + ((tid >> 3) & 1) * 2 + ((tid >> 2) & 1);
   float4 w[7];
 #pragma unroll
   for (int j = 0; j < 7; ++j) w[j] = __ldg(reinterpret_cast<const float4*>(dw_w + (size_t)j * C + c));
   const float4 bias = __ldg(reinterpret_cast<const float4*>(dw_b + c));
   const float4 gw = __ldg(reinterpret_cast<const float4*>(ln_w + c));
   const float4 gb = __ldg(reinterpret_cast<const float4*>(ln_b + c));
-  auto load_row = [&](int t) -> float4 {
-    return (t >= 0 && t < T) ? __ldg(reinterpret_cast<const float4*>(ib + (size_t)t * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  };
-  float4 x[7 + R - 1];  // window: x[k] = row t0 - 3 + k
-  float4 nx[R];         // the R new rows of the NEXT batch, prefetched while this batch is reduced and stored
+  const uint8_t* col = dsm + (size_t)c * 4;  // this thread's 4-channel column
+  float4 x[14];                              // window: x[i] = row 8m-3+i of the clip
+  int q = 0, cs = 0;                         // ring index / slot / phase of the chunk holding rows 8m-3 .. 8m+4
+  uint32_t cph = 0;
+  bool first = true;
+
+  auto step = [&](const bool fresh) {
+    const int g0 = R * m - 3;
+    const bool interior = g0 >= 0 && g0 + 14 <= T;  // every window row exists in the clip
+    int cs1 = cs + 1;
+    uint32_t cph1 = cph;
+    if (cs1 == NST) {
+      cs1 = 0;
+      cph1 ^= 1u;
+    }
+    const uint8_t* s0 = col + (size_t)cs * STAGE_BYTES;
+    const uint8_t* s1 = col + (size_t)cs1 * STAGE_BYTES;
+    if (fresh) ptx::mbar_wait(&full[cs], cph);
+    if (interior) {
+      if (fresh) {
 #pragma unroll
-  for (int k = 0; k < 6; ++k) x[k] = load_row(t_begin - 3 + k);
-  if constexpr (PREFETCH) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) nx[r] = load_row(t_begin + 3 + r);
-  }
-  for (int t0 = t_begin; t0 < t_end; t0 += R) {
-    if constexpr (PREFETCH) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) x[6 + r] = nx[r];
-      if (t0 + R < t_end) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) nx[r] = load_row(t0 + R + 3 + r);
+        for (int i = 0; i < 6; ++i) x[i] = *reinterpret_cast<const float4*>(s0 + i * ROW_BYTES);
       }
-    } else {
 #pragma unroll
-      for (int r = 0; r < R; ++r) x[6 + r] = load_row(t0 + 3 + r);
+      for (int i = 6; i < 8; ++i) x[i] = *reinterpret_cast<const float4*>(s0 + i * ROW_BYTES);
+      ptx::mbar_wait(&full[cs1], cph1);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) x[8 + i] = *reinterpret_cast<const float4*>(s1 + i * ROW_BYTES);
+    } else {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fresh) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int t = g0 + i;
+          x[i] = (t >= 0 && t < T) ? *reinterpret_cast<const float4*>(s0 + i * ROW_BYTES) : z;
+        }
+      }
+#pragma unroll
+      for (int i = 6; i < 8; ++i) {
+        const int t = g0 + i;
+        x[i] = (t >= 0 && t < T) ? *reinterpret_cast<const float4*>(s0 + i * ROW_BYTES) : z;
+      }
+      ptx::mbar_wait(&full[cs1], cph1);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int t = g0 + 8 + i;
+        x[8 + i] = (t >= 0 && t < T) ? *reinterpret_cast<const float4*>(s1 + i * ROW_BYTES) : z;
+      }
     }
     float4 y[R];
-    float s[R];
+    float sv[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       float2 lo = make_float2(bias.x, bias.y), hi = make_float2(bias.z, bias.w);
 #pragma unroll
-      for (int j = 0; j < 7; ++j) {  // packed fp32 FMA: 14 FFMA2 instead of 28 FFMA per row
+      for (int j = 0; j < 7; ++j) {
         lo = ffma2(make_float2(x[r + j].x, x[r + j].y), make_float2(w[j].x, w[j].y), lo);
         hi = ffma2(make_float2(x[r + j].z, x[r + j].w), make_float2(w[j].z, w[j].w), hi);
       }
       y[r] = make_float4(lo.x, lo.y, hi.x, hi.y);
       const float2 sm = fadd2(lo, hi);
-      s[r] = sm.x + sm.y;
+      sv[r] = sm.x + sm.y;
     }
     {
-      const float tot = warp_sum8(s, lane);
+      const float tot = warp_sum8(sv, lane);
       if ((lane & 3) == 0) red[0][my_row][warp] = tot;
     }
     __syncthreads();
-    float mean[R], q[R];
+    const bool clip_end = m == nbT - 1;
+    // every thread has read chunk q (and, at the end of a clip, what it needs of chunk q + 1): refill their slots
+    if (tid == 0) issue_upto((clip_end ? q + 1 : q) + NST);
+    {
+      const float4 p0 = *reinterpret_cast<const float4*>(&red[0][lane & 7][0]), p1 = *reinterpret_cast<const float4*>(&red[0][lane & 7][4]);
+      const float mine = (((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w))) * (-1.f / C);
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float4 p0 = *reinterpret_cast<const float4*>(&red[0][r][0]), p1 = *reinterpret_cast<const float4*>(&red[0][r][4]);
-      mean[r] = (((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w))) * (1.f / C);
-      const float2 nm = make_float2(-mean[r], -mean[r]);
-      const float2 dl = fadd2(make_float2(y[r].x, y[r].y), nm), dh = fadd2(make_float2(y[r].z, y[r].w), nm);
-      y[r] = make_float4(dl.x, dl.y, dh.x, dh.y);  // keep the centred values
-      const float2 sq = ffma2(dh, dh, fmul2(dl, dl));
-      q[r] = sq.x + sq.y;
+      for (int r = 0; r < R; ++r) {
+        const float nmean = __shfl_sync(0xffffffffu, mine, r);
+        const float2 nm = make_float2(nmean, nmean);
+        const float2 dl = fadd2(make_float2(y[r].x, y[r].y), nm), dh = fadd2(make_float2(y[r].z, y[r].w), nm);
+        y[r] = make_float4(dl.x, dl.y, dh.x, dh.y);  // keep the centred values
+        const float2 sq = ffma2(dh, dh, fmul2(dl, dl));
+        sv[r] = sq.x + sq.y;
+      }
     }
     {
-      const float tot = warp_sum8(q, lane);
+      const float tot = warp_sum8(sv, lane);
       if ((lane & 3) == 0) red[1][my_row][warp] = tot;
     }
     __syncthreads();
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float4 p0 = *reinterpret_cast<const float4*>(&red[1][r][0]), p1 = *reinterpret_cast<const float4*>(&red[1][r][4]);
+    {
+      const float4 p0 = *reinterpret_cast<const float4*>(&red[1][lane & 7][0]), p1 = *reinterpret_cast<const float4*>(&red[1][lane & 7][4]);
       const float v = ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w));
-      const float rstd = rsqrtf(v * (1.f / C) + 1e-6f);
-      const int t = t0 + r;
-      if (t < t_end) {
+      const float mine = rsqrtf(v * (1.f / C) + 1e-6f);
+      TOut* ob = out + ((size_t)b * T + (size_t)R * m) * C + c;
+      auto emit = [&](int r, float rstd) {
         const float2 rs = make_float2(rstd, rstd);
         const float2 ol = ffma2(fmul2(make_float2(y[r].x, y[r].y), rs), make_float2(gw.x, gw.y), make_float2(gb.x, gb.y));
         const float2 oh = ffma2(fmul2(make_float2(y[r].z, y[r].w), rs), make_float2(gw.z, gw.w), make_float2(gb.z, gb.w));
-        const float4 o = make_float4(ol.x, ol.y, oh.x, oh.y);
         if constexpr (sizeof(TOut) == 4) {
-          *reinterpret_cast<float4*>(ob + (size_t)t * C) = o;
+          *reinterpret_cast<float4*>(ob + (size_t)r * C) = make_float4(ol.x, ol.y, oh.x, oh.y);
         } else {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+          __nv_bfloat162 lo = __floats2bfloat162_rn(ol.x, ol.y), hi = __floats2bfloat162_rn(oh.x, oh.y);
           uint2 pk;
           pk.x = *reinterpret_cast<uint32_t*>(&lo);
           pk.y = *reinterpret_cast<uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(ob + (size_t)t * C) = pk;
+          *reinterpret_cast<uint2*>(ob + (size_t)r * C) = pk;
+        }
+      };
+      if (R * m + R <= T) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) emit(r, __shfl_sync(0xffffffffu, mine, r));
+      } else {
+        const int rows_here = T - R * m;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float rstd = __shfl_sync(0xffffffffu, mine, r);
+          if (r < rows_here) emit(r, rstd);
         }
       }
     }
-    // slide the window by R rows; the next batch's writes to red[0] are ordered after this batch's reads of red[0]
-    // by the second __syncthreads above, and its writes to red[1] after these reads by its own first __syncthreads
+    // slide the window by R rows (red[0] of the next batch is written after this batch's second __syncthreads,
+    // i.e. after every read of red[0] above; its red[1] writes come after its own first __syncthreads)
 #pragma unroll
-    for (int k = 0; k < 6; ++k) x[k] = x[k + R];
+    for (int i = 0; i < 6; ++i) x[i] = x[i + R];
+    // advance to the next item: at the end of a clip two chunks are consumed (q and the mostly-padding q + 1)
+    const int adv = clip_end ? 2 : 1;
+    q += adv;
+    for (int a = 0; a < adv; ++a) {
+      if (++cs == NST) {
+        cs = 0;
+        cph ^= 1u;
+      }
+    }
+    if (clip_end) {
+      m = 0;
+      ++b;
+    } else {
+      ++m;
+    }
+  };
+
+  for (long long left = i1 - i0; left > 0; --left) {
+    const bool fresh = first || m == 0;
+    first = false;
+    step(fresh);
   }
 }
 
-template <int C>
-static int dwconv_ln_run_dispatch(const float* in, const float* dw_w, const float* dw_b, const float* ln_w,
-                                  const float* ln_b, void* out, int out_dt, int B, int T, cudaStream_t st) {
-  const int run = 64;  // rows per block (6 halo rows are re-read per run; 128 measured slower: fewer, longer blocks)
-  dim3 grid((T + run - 1) / run, B);
+template <int C, int NST, int MINB>
+static int dwconv_ln_stream_dispatch(const float* in, const float* dw_w, const float* dw_b, const float* ln_w,
+                                      const float* ln_b, void* out, int out_dt, int B, int T, cudaStream_t st) {
+  const long long items = (long long)B * ((T + 7) / 8);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    DC_CUDA(cudaGetDevice(&dev));
+    DC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const unsigned grid = (unsigned)std::min<long long>(items, (long long)sms * MINB);
+  const size_t smem = (size_t)NST * 8 * C * 4;
   ProfScope ps(PC_DWCONV_LN, 0, (double)B * T * C * (4.0 + (out_dt == DT_F32 ? 4.0 : 2.0)), st, "C%d", C);
-  if (out_dt == DT_F32)
-    dwconv_ln_run_kernel<C, float><<<grid, C / 4, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (float*)out, T, run);
-  else
-    dwconv_ln_run_kernel<C, __nv_bfloat16><<<grid, C / 4, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (__nv_bfloat16*)out, T, run);
+  if (out_dt == DT_F32) {
+    auto k = dwconv_ln_stream_kernel<C, float, NST, MINB>;
+    static bool attr = false;
+    if (!attr) { DC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    k<<<grid, C / 4, smem, st>>>(in, dw_w, dw_b, ln_w, ln_b, (float*)out, B, T);
+  } else {
+    auto k = dwconv_ln_stream_kernel<C, __nv_bfloat16, NST, MINB>;
+    static bool attr = false;
+    if (!attr) { DC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    k<<<grid, C / 4, smem, st>>>(in, dw_w, dw_b, ln_w, ln_b, (__nv_bfloat16*)out, B, T);
+  }
   ++g_launches_pw;
   DC_CUDA(cudaGetLastError());
   return DC_OK;
@@ -295,7 +411,7 @@ static int dwconv_ln_dispatch(const float* in, const float* dw_w, const float* d
   constexpr int C = VPL * 128;
   ProfScope ps(dw_w ? PC_DWCONV_LN : PC_LAYERNORM, 0, (double)rows * C * (4.0 + (out_dt == DT_F32 ? 4.0 : 2.0)), st,
                "C%d", C);
-  // LayerNorm only (the stem / inter-stage / final norms); depthwise conv + LN goes to dwconv_ln_run_kernel
+  // LayerNorm only (the stem / inter-stage / final norms); depthwise conv + LN goes to dwconv_ln_stream_kernel
   if (out_dt == DT_F32) dwconv_ln_kernel<VPL, false, float><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (float*)out, B, T);
   else dwconv_ln_kernel<VPL, false, __nv_bfloat16><<<grid, 256, 0, st>>>(in, dw_w, dw_b, ln_w, ln_b, (__nv_bfloat16*)out, B, T);
   ++g_launches_pw;
@@ -305,12 +421,12 @@ static int dwconv_ln_dispatch(const float* in, const float* dw_w, const float* d
 
 int launch_dwconv_ln(const float* in, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b,
                      void* out, int out_dt, int B, int T, int C, cudaStream_t st) {
-  if (dw_w) {  // depthwise conv + LN: sliding-window kernel
+  if (dw_w) {  // depthwise conv + LN: streaming kernel; <C, ring depth, CTAs per SM> (128 registers x C/4 threads)
     switch (C) {
-      case 256: return dwconv_ln_run_dispatch<256>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
-      case 512: return dwconv_ln_run_dispatch<512>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
-      case 768: return dwconv_ln_run_dispatch<768>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
-      case 1024: return dwconv_ln_run_dispatch<1024>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
+      case 256: return dwconv_ln_stream_dispatch<256, 3, 8>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
+      case 512: return dwconv_ln_stream_dispatch<512, 3, 4>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
+      case 768: return dwconv_ln_stream_dispatch<768, 3, 2>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
+      case 1024: return dwconv_ln_stream_dispatch<1024, 3, 2>(in, dw_w, dw_b, ln_w, ln_b, out, out_dt, B, T, st);
       default: set_error("dwconv_ln: unsupported channel count %d (256/512/768/1024)", C); return DC_ERR_SHAPE;
     }
   }
