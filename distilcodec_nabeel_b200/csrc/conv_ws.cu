@@ -389,11 +389,9 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 bb = *reinterpret_cast<const float2*>(sb1 + c * 32 + g * 8 + 2 * e);
-            float v0 = __uint_as_float(acc[g * 8 + 2 * e]) + bb.x;
-            float v1 = __uint_as_float(acc[g * 8 + 2 * e + 1]) + bb.y;
-            v0 = inside ? silu_fast(v0) : 0.f;
-            v1 = inside ? silu_fast(v1) : 0.f;
-            __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+            float2 v = silu_fast2(fadd2(make_float2(__uint_as_float(acc[g * 8 + 2 * e]), __uint_as_float(acc[g * 8 + 2 * e + 1])), bb));
+            if (!inside) v = make_float2(0.f, 0.f);
+            __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
             pk[e] = *reinterpret_cast<uint32_t*>(&h);
           }
           const int chunk = c * 4 + g;
