@@ -227,3 +227,28 @@ def test_large_batch_is_deterministic_and_batch_invariant():
     assert torch.equal(c1[:8], c1[8:16]) and torch.equal(w1[:8], w1[56:64])   # repeated clips, different tiles/CTAs
     c3, w3 = pipe.reconstruct_device(mel[:3].contiguous())
     assert torch.equal(c3, c1[:3]) and torch.equal(w3, w1[:3])
+
+
+def test_ten_minute_clips_tokenize_then_decode_host_buffers():
+    """BASELINE configs[4] at its real clip length: 10-minute clips (T = 56,250 frames, 14.4 M samples each) through the
+    host-buffer legs (tokenize = wav->codes leg from log-mel, decode = codes->wav leg).  The oracle cannot run this size
+    in seconds, so the check is the size-independent window property against the same engine on a short cut (which the
+    golden tests tie to the reference): identical codes and waveform in the window's interior."""
+    from distilcodec_nabeel_b200.sharding import Pipeline
+    eng = engine("W1", "bf16")
+    T = 56250
+    mel = make_mel(2, 1500, seed=5).repeat(1, 1, 38)[:, :, :T].contiguous().pin_memory()   # periodic, ragged vs every tile
+    pipe = Pipeline(eng)
+    codes = pipe.tokenize(mel)
+    assert codes.shape == (2, T) and codes.dtype == torch.int64
+    wav = pipe.decode(codes)
+    assert wav.shape == (2, T * 256) and bool(torch.isfinite(wav).all())
+    a0, a1, margin = 40000, 41200, 200
+    m = mel[:, :, a0:a1].contiguous().to(eng.device)
+    c_win, _ = pipe.encode_device(m)
+    assert torch.equal(c_win[:, margin:-margin].cpu(), codes[:, a0 + margin:a1 - margin])
+    w_win = pipe.decode_device(codes[:, a0:a1].contiguous().to(eng.device)).cpu()
+    w_full = wav[:, (a0 + margin) * 256:(a1 - margin) * 256]
+    assert rel_err(w_win[:, margin * 256:-margin * 256], w_full) < 1e-5
+    # the input is periodic with period 1500 frames: so are the codes away from the clip ends
+    assert torch.equal(codes[:, 3000:4500], codes[:, 33000:34500])
