@@ -10,6 +10,7 @@ from .engine import Engine, load_config
 from .modules import (B200Encoder, B200Generator, B200MelSpectrogram, B200Quantizer, EngineSet, GRVQResult,
                       build_modules, mel_buffers, patch)
 from .sharding import Pipeline, shard_clips, gather_by_clip
+from . import bulk
 
 __all__ = ["Engine", "EngineSet", "B200Encoder", "B200Quantizer", "B200Generator", "GRVQResult", "Pipeline",
            "build_modules", "patch", "B200MelSpectrogram", "mel_buffers", "load_config", "shard_clips", "gather_by_clip", "_abi"]

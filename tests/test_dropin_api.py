@@ -119,3 +119,33 @@ def test_mel_frontend_patch_and_buffers(codecs):
     c = patch(ref_loader.build_reference_codec(sd, codebook_size=1024), device="cpu", mel_frontend=True)
     assert isinstance(c.spec_transform, B200MelSpectrogram)
     assert "spec_transform.fb" in c.encoder._engines.state_dict
+
+
+def test_bulk_encode_is_result_identical_to_reference_encode(codecs):
+    """distilcodec_nabeel_b200.bulk.encode against DistilCodec.encode (distil_codec.py:545-573):
+    same GRVQResult, the SAME token dict objects, same per-clip feature tensors, same lengths; features=False only
+    empties the two feature lists."""
+    from distilcodec_nabeel_b200 import bulk
+    ref, patched = codecs
+    clips = [[_pcm(1.0), 24000], [_pcm(0.6), 24000], [_pcm(0.3), 24000]]
+    with torch.no_grad():
+        r0, gen0, hop0 = ref.encode(copy.deepcopy(clips), enable_bfloat16=False, raw_audio=True)
+    r1, gen1, hop1 = bulk.encode(patched, copy.deepcopy(clips), enable_bfloat16=False, raw_audio=True)
+    assert gen0 == gen1 and hop0 == hop1
+    assert torch.equal(r0.codes, r1.codes)
+    assert r0.codes_list == r1.codes_list and [len(c) for c in r1.codes_list] == hop1
+    table = patched.gr_audio_code2token["g0r0"]["audio_code_token"]
+    assert all(tok is table[str(tok["in_codebook_id"])] for tok in r1.codes_list[1])
+    assert len(r1.x_pjt_in_list) == len(r1.quantized_fup_list) == 3
+    for a, b in zip(r0.x_pjt_in_list + r0.quantized_fup_list, r1.x_pjt_in_list + r1.quantized_fup_list):
+        assert a.shape == b.shape and a.dtype == b.dtype and torch.allclose(a, b, atol=1e-5)
+    r2, _, _ = bulk.encode(patched, copy.deepcopy(clips), raw_audio=True, features=False)
+    assert r2.codes_list == r0.codes_list and r2.x_pjt_in_list == [] and r2.quantized_fup_list == []
+    # generic (groups, residual levels) ordering of audio_tokenize: frame-major, then group, then level
+    fake = copy.copy(patched)
+    fake.gr_audio_code2token = {f"g{g}r{r}": {"audio_code_token": {str(n): (g, r, n) for n in range(5)}}
+                                for g in range(2) for r in range(3)}
+    codes = np.arange(2 * 4 * 3).reshape(2, 4, 3) % 5
+    flat = torch.from_numpy(codes).transpose(1, 0).reshape(4, 6).flatten().tolist()      # as distil_codec.py:563
+    want = ref.audio_tokenize.__func__(fake, codes=flat, n_groups=2, n_residual=3)
+    assert bulk.tokenize_codes(fake, codes) == want

@@ -83,3 +83,28 @@ def test_state_dict_round_trip_and_codebooks_view(codec):
     assert codec.quantizer.downsample_factor == [1]
     with pytest.raises(RuntimeError):
         codec.encoder.load_state_dict({"bogus": torch.zeros(1)})
+
+
+def test_bulk_encode_on_the_device(codec):
+    """bulk.encode (row f-2) on the real kernels: pinned asynchronous D2H of codes and per-clip features, vectorised
+    token mapping.  Checked against the straightforward per-clip `.cpu()` slicing DistilCodec.encode does
+    (distil_codec.py:556-570) on the same quantizer output."""
+    from distilcodec_nabeel_b200 import bulk
+    from tests.golden.inputs import make_mel
+    hops = [40, 17, 33]
+    mel = make_mel(3, 40, seed=21).cuda()
+    codec.gr_audio_code2token = {"g0r0": {"codebook_size": 32768, "audio_code_token": {
+        str(n): {"content": f"<|g0r0_{n}|>", "absolute_token_id": n, "in_codebook_id": n} for n in range(32768)}}}
+    codec.preprocess_raw_audio_batch = lambda clips: (None, mel, [h * 256 / 24000 for h in hops], hops)
+    for bf16 in (False, True):
+        ret, _, hop_out = bulk.encode(codec, [None] * 3, enable_bfloat16=bf16, raw_audio=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+            want = codec.quantizer(codec.encoder(mel))
+        assert hop_out == hops and torch.equal(ret.codes, want.codes)
+        for b, h in enumerate(hops):
+            ids = want.codes[0, b, :h, 0].cpu().tolist()
+            assert [t["in_codebook_id"] for t in ret.codes_list[b]] == ids
+            assert torch.equal(ret.x_pjt_in_list[b], want.x_pjt_in[b, :h].reshape(h, 2, -1).reshape(h * 2, -1).cpu())
+            assert torch.equal(ret.quantized_fup_list[b],
+                               want.quantized_fup[b, :h].reshape(h, 2, -1).reshape(h * 2, -1).cpu())
+            assert not ret.x_pjt_in_list[b].is_cuda and ret.x_pjt_in_list[b].shape == (2 * h, 1792)
