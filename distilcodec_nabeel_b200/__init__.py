@@ -9,7 +9,7 @@ from . import _abi
 from .engine import Engine, load_config
 from .modules import (B200Encoder, B200Generator, B200MelSpectrogram, B200Quantizer, EngineSet, GRVQResult,
                       build_modules, mel_buffers, patch)
-from .sharding import Pipeline, shard_clips, gather_by_clip
+from .sharding import Pipeline, shard_clips, gather_by_clip, tokenize_long, decode_long, time_tiles
 from . import bulk
 
 __all__ = ["Engine", "EngineSet", "B200Encoder", "B200Quantizer", "B200Generator", "GRVQResult", "Pipeline",

@@ -208,6 +208,55 @@ class Pipeline:
         return wav_out
 
 
+# ---- time tiling (SURVEY.md section 8 row f-3): clips longer than one workspace -------------------------------------
+# The path has a finite receptive field and no global-in-time operation: encoder = stem k7 + 18 ConvNeXt depthwise k7
+# (models/encoders.py:8-76) -> +-57 frames, quantizer pre/post blocks +-6 each (grfvq.py:28-103), decoder conv_pre k7 +
+# 5 ConvTranspose/ResBlock stages (models/generators.py:29-147) -> < +-25 frames.  A time tile computed with HALO real
+# frames of context on each side (clip ends keep the convs' zero padding) therefore reproduces the whole-clip result
+# on its interior; every output element is produced by the same instruction sequence wherever its tile starts, so the
+# match is bit-exact (tests/test_gpu_e2e.py).
+ENCODE_HALO = 96
+DECODE_HALO = 48
+
+
+def time_tiles(T: int, tile: int, halo: int):
+    """[(lo, hi, s, e)]: compute frames [lo, hi) to obtain frames [s, e); tiles cover [0, T) in order."""
+    if tile <= 0:
+        raise ValueError("tile must be positive")
+    out = []
+    for s in range(0, T, tile):
+        e = min(T, s + tile)
+        out.append((max(0, s - halo), min(T, e + halo), s, e))
+    return out
+
+
+def tokenize_long(pipe: "Pipeline", mel_host: torch.Tensor, tile: int = 8192,
+                  codes_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """wav->codes leg for clips of any length with device memory bounded by `tile` frames: HOST log-mel (B,128,T) ->
+    host codes (B,T), identical to `Pipeline.tokenize` on the whole clip."""
+    B, _, T = mel_host.shape
+    if codes_out is None:
+        codes_out = torch.empty(B, T, dtype=torch.int64, pin_memory=True)
+    for lo, hi, s, e in time_tiles(T, tile, ENCODE_HALO):
+        c = pipe.tokenize(mel_host[:, :, lo:hi].contiguous())
+        codes_out[:, s:e] = c[:, s - lo:e - lo]
+    return codes_out
+
+
+def decode_long(pipe: "Pipeline", codes_host: torch.Tensor, tile: int = 8192,
+                wav_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """codes->wav leg for clips of any length: HOST codes (B,T) -> host waveform (B, hop*T), identical to
+    `Pipeline.decode` on the whole clip."""
+    B, T = codes_host.shape
+    hop = pipe.eng.hop
+    if wav_out is None:
+        wav_out = torch.empty(B, T * hop, dtype=torch.float32, pin_memory=True)
+    for lo, hi, s, e in time_tiles(T, tile, DECODE_HALO):
+        w = pipe.decode(codes_host[:, lo:hi].contiguous())
+        wav_out[:, s * hop:e * hop] = w[:, (s - lo) * hop:(e - lo) * hop]
+    return wav_out
+
+
 def run_sharded(fn, items: Sequence, world_size: int, rank: int):
     """Apply `fn` to this rank's shard of `items` (a list of clips) and return (indices, results)."""
     idx = shard_clips(len(items), world_size, rank)

@@ -252,3 +252,17 @@ def test_ten_minute_clips_tokenize_then_decode_host_buffers():
     assert rel_err(w_win[:, margin * 256:-margin * 256], w_full) < 1e-5
     # the input is periodic with period 1500 frames: so are the codes away from the clip ends
     assert torch.equal(codes[:, 3000:4500], codes[:, 33000:34500])
+
+
+def test_time_tiled_legs_are_bit_identical_to_whole_clip():
+    """Row f-3: tokenize_long / decode_long (time tiles with real-context halos) against the whole-clip legs."""
+    from distilcodec_nabeel_b200.sharding import Pipeline, decode_long, tokenize_long
+    eng = engine("W1", "bf16")
+    pipe = Pipeline(eng)
+    mel = make_mel(2, 4100, seed=9).pin_memory()
+    codes = pipe.tokenize(mel)
+    for tile in (1000, 1537, 4100, 9000):
+        assert torch.equal(tokenize_long(pipe, mel, tile=tile), codes), tile
+    wav = pipe.decode(codes)
+    for tile in (1000, 1537):
+        assert torch.equal(decode_long(pipe, codes, tile=tile), wav), tile

@@ -74,3 +74,15 @@ def test_world_size_2_gloo_gather_restores_input_order(n_clips):
         assert full == expect                      # unsharded result, bit for bit, on every rank
         assert codes == list(range(n_clips))
         assert (only0 == expect) if rank == 0 else (only0 is None)
+
+
+def test_time_tiles_cover_the_clip_in_order():
+    from distilcodec_nabeel_b200.sharding import time_tiles
+    for T, tile, halo in ((10, 4, 3), (4100, 1000, 96), (7, 100, 5), (8192, 8192, 96), (1, 1, 0)):
+        tiles = time_tiles(T, tile, halo)
+        assert tiles[0][2] == 0 and tiles[-1][3] == T
+        for (lo, hi, s, e), nxt in zip(tiles, tiles[1:] + [None]):
+            assert 0 <= lo <= s < e <= hi <= T and s - lo <= halo and hi - e <= halo
+            assert (lo == 0 or s - lo == halo) and (hi == T or hi - e == halo)
+            if nxt:
+                assert nxt[2] == e
