@@ -378,26 +378,25 @@ template <int C, int NST, int MINB>
 static int dwconv_ln_stream_dispatch(const float* in, const float* dw_w, const float* dw_b, const float* ln_w,
                                       const float* ln_b, void* out, int out_dt, int B, int T, cudaStream_t st) {
   const long long items = (long long)B * ((T + 7) / 8);
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    DC_CUDA(cudaGetDevice(&dev));
-    DC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int dev = 0, sms = 0;
+  DC_CUDA(cudaGetDevice(&dev));
+  DC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const unsigned grid = (unsigned)std::min<long long>(items, (long long)sms * MINB);
   const size_t smem = (size_t)NST * 8 * C * 4;
   ProfScope ps(PC_DWCONV_LN, 0, (double)B * T * C * (4.0 + (out_dt == DT_F32 ? 4.0 : 2.0)), st, "C%d", C);
-  if (out_dt == DT_F32) {
-    auto k = dwconv_ln_stream_kernel<C, float, NST, MINB>;
-    static bool attr = false;
-    if (!attr) { DC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    k<<<grid, C / 4, smem, st>>>(in, dw_w, dw_b, ln_w, ln_b, (float*)out, B, T);
-  } else {
-    auto k = dwconv_ln_stream_kernel<C, __nv_bfloat16, NST, MINB>;
-    static bool attr = false;
-    if (!attr) { DC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    k<<<grid, C / 4, smem, st>>>(in, dw_w, dw_b, ln_w, ln_b, (__nv_bfloat16*)out, B, T);
+  static unsigned attr_dev_mask[2] = {0u, 0u};  // the opt-in shared-memory size is a per-device function attribute
+  const int which = out_dt == DT_F32 ? 0 : 1;
+  if (!(attr_dev_mask[which] & (1u << dev))) {
+    if (which == 0)
+      DC_CUDA(cudaFuncSetAttribute(dwconv_ln_stream_kernel<C, float, NST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      DC_CUDA(cudaFuncSetAttribute(dwconv_ln_stream_kernel<C, __nv_bfloat16, NST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev_mask[which] |= 1u << dev;
   }
+  if (which == 0)
+    dwconv_ln_stream_kernel<C, float, NST, MINB><<<grid, C / 4, smem, st>>>(in, dw_w, dw_b, ln_w, ln_b, (float*)out, B, T);
+  else
+    dwconv_ln_stream_kernel<C, __nv_bfloat16, NST, MINB><<<grid, C / 4, smem, st>>>(in, dw_w, dw_b, ln_w, ln_b, (__nv_bfloat16*)out, B, T);
   ++g_launches_pw;
   DC_CUDA(cudaGetLastError());
   return DC_OK;

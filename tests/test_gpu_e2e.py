@@ -266,3 +266,20 @@ def test_time_tiled_legs_are_bit_identical_to_whole_clip():
     wav = pipe.decode(codes)
     for tile in (1000, 1537):
         assert torch.equal(decode_long(pipe, codes, tile=tile), wav), tile
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process_agree():
+    """Engines on cuda:0 and cuda:1 of the same process (per-device function attributes, tensor maps, workspaces):
+    identical results."""
+    from distilcodec_nabeel_b200 import Engine
+    from distilcodec_nabeel_b200.sharding import Pipeline
+    sd = state_dict("W1")
+    mel = make_mel(3, 300, seed=31)
+    outs = []
+    for d in (0, 1):
+        eng = Engine(sd, d, "bf16")
+        c, w = Pipeline(eng).reconstruct_device(mel.to(eng.device))
+        outs.append((c.cpu(), w.cpu()))
+        eng.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
