@@ -7,7 +7,7 @@ second, encode+decode).
 A step = one pass of the hot path (mel -> ConvNeXt encoder -> 32768x3584 VQ -> HiFiGAN decoder -> wav) over one
 batch of synthetic clips: BASELINE configs[3], "full encode->decode reconstruction, 256 synthetic 10 s clips", per
 GPU (weak scaling: clips shard across ranks, no data-path collective).  Weights are random-init of the architecture
-in configs/model_config.json (oracle/weights.py, W0 — the HF checkpoint is not available offline).
+in configs/model_config.json (distilcodec_nabeel_b200/random_init.py, W0 — the HF checkpoint is not available offline).
 
 Prints ONE JSON line (rank 0):
   value        whole-job audio-s/s with the mel batch already resident in HBM, CUDA-event timed, max over ranks
@@ -193,7 +193,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from distilcodec_nabeel_b200 import Engine, Pipeline
-    from oracle import weights                      # weight generator only (test infrastructure, not the timed path)
+    from distilcodec_nabeel_b200 import random_init as weights   # synthetic W0 weights (no oracle/ import in this arm)
     from tests.golden.inputs import make_mel
 
     K, W = args.steps, max(args.warmup, 3)

@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from distilcodec_nabeel_b200 import Engine
-from oracle import weights
+from distilcodec_nabeel_b200 import random_init as weights
 from tests.golden.inputs import make_mel
 
 stage = sys.argv[1] if len(sys.argv) > 1 else "encoder"

@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from distilcodec_nabeel_b200 import Engine
-from oracle import weights
+from distilcodec_nabeel_b200 import random_init as weights
 from tests.golden.inputs import make_vq_rows
 
 sd = weights.make_state_dict("W0")

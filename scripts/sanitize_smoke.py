@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from distilcodec_nabeel_b200 import Engine, load_config, mel_buffers
-from oracle import weights
+from distilcodec_nabeel_b200 import random_init as weights
 from tests.golden.inputs import make_mel, make_wav
 
 sd = dict(weights.make_state_dict("W1", codebook_size=1024))
