@@ -321,6 +321,7 @@ conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m_blk = tile / n_tiles, n0 = (tile % n_tiles) * BN;
       const int clip = m_blk / tiles_per_clip, t0 = (m_blk % tiles_per_clip) * 128;
       const int p = it & 1;
+      epilogue_prefetch(ep, clip, s.T, t0 + (wg & 3) * 32, n0 + ((wg - 2) >> 2) * (BN / 2), BN / 2, lane);
       ptx::mbar_wait_sleepy(&tfull[p], (it >> 1) & 1);
       ptx::tc_fence_after();
       epilogue_tile<BN, CW>(ep, variant, stg, tmem_base + p * BN, clip, t0, n0, s.T, wg, lane);
@@ -386,7 +387,9 @@ static int launch_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
     ProfScope ps(PC_CONV_TS, 2.0 * macs, rows * s.C * 2.0 + (double)s.N * s.J * s.C * 2.0 + rows * s.N * out_bytes, st,
                  "w<%d,%d,%d>|C%d N%d J%d d%d e%d", EG, CW, BST, s.C, s.N, s.J, s.dil, esig);
     Epilogue eg = e;
-    eg.prefetch = 0;
+    // L2-prefetching the residual tile while the MMAs run pays only where the layer is HBM-latency-bound (A/B on one
+    // box: k = 3 at C = 256 -6 % / -11 %; k = 7 +9 %; the tensor-bound k = 11 layers lose ~3 %)
+    eg.prefetch = (s.J * s.C <= 768) ? e.prefetch : 0;
     conv_tsw_kernel<EG, CW, BST><<<grid, 64 + EG * 256, TOTAL, st>>>(tmA, tmW, s, eg, epilogue_variant(e), tiles_per_clip,
                                                             (int)m_tiles, n_tiles);
   }
