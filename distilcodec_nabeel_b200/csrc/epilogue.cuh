@@ -306,6 +306,65 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int variant, f
     __syncwarp();
   }
 }
+// ---------------------------------------------------------------- direct epilogue for TRANSPOSED accumulators
+// conv_ts computes D^T (TMEM lane = output channel, column = time row): after tcgen05.ld a lane holds 32 consecutive
+// ROWS of ONE channel, and the 32 lanes of the warp are 32 consecutive channels = the contiguous dimension of the
+// channels-last tensors.  A warp-wide 4-byte access per row is therefore one full 128-byte line (fp32) / one 64-byte
+// segment (bf16): coalesced with no shared-memory transpose at all.  ncu (prof_r1_ts3) showed the shared-memory data
+// pipe 63 % busy on the short-K C = 128 layers with a third of it the epilogue's transpose traffic.
+// acc: 32 rows (t_first ..) of this lane's channel; off0: element offset of (t_first, channel); nvalid: rows with t < T.
+template <int V>
+__device__ __forceinline__ void epilogue_rows_direct(const Epilogue& ep, const uint32_t (&acc)[32], size_t off0, int nvalid,
+                                                     float bias) {
+  constexpr bool kRes = V == EV_RES_F32_BF16S || V == EV_RES_F32 || V == EV_RES_MEAN_BF16S;
+  constexpr bool kOut0F = V == EV_RES_F32_BF16S || V == EV_RES_F32 || V == EV_F32_BF16S || V == EV_F32;
+  constexpr bool kOut0B = V == EV_SILU_BF16 || V == EV_BF16;
+  constexpr bool kOut1 = V == EV_RES_F32_BF16S || V == EV_RES_MEAN_BF16S || V == EV_F32_BF16S;
+  constexpr int G = 8;  // rows per batch: G residual (+ 2G mean operand) loads in flight per lane
+  const size_t ld = (size_t)ep.ldo;
+  const float2 b2 = make_float2(bias, bias);
+#pragma unroll
+  for (int g0 = 0; g0 < 32; g0 += G) {
+    if (g0 >= nvalid) break;  // warp-uniform
+    float r[G], a1[G], a2[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const bool ok = g0 + i < nvalid;
+      const size_t off = off0 + (size_t)(g0 + i) * ld;
+      if constexpr (kRes) r[i] = ok ? reinterpret_cast<const float*>(ep.res)[off] : 0.f;
+      if constexpr (V == EV_RES_MEAN_BF16S) {
+        a1[i] = ok ? __ldg(reinterpret_cast<const float*>(ep.add1) + off) : 0.f;
+        a2[i] = ok ? __ldg(reinterpret_cast<const float*>(ep.add2) + off) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < G; i += 2) {
+      float2 v = fadd2(make_float2(__uint_as_float(acc[g0 + i]), __uint_as_float(acc[g0 + i + 1])), b2);
+      if constexpr (V == EV_SILU_BF16) v = silu_fast2(v);
+      if constexpr (kRes) v = fadd2(v, make_float2(r[i], r[i + 1]));
+      if constexpr (V == EV_RES_MEAN_BF16S)
+        v = fmul2(fadd2(fadd2(v, make_float2(a1[i], a1[i + 1])), make_float2(a2[i], a2[i + 1])), make_float2(ep.scale, ep.scale));
+      float2 sv = v;
+      if constexpr (kOut1) sv = silu_fast2(v);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (g0 + i + h < nvalid) {  // warp-uniform
+          const size_t off = off0 + (size_t)(g0 + i + h) * ld;
+          const float x = h ? v.y : v.x, sx = h ? sv.y : sv.x;
+          if constexpr (kOut0F) reinterpret_cast<float*>(ep.out0)[off] = x;
+          if constexpr (kOut0B) reinterpret_cast<__nv_bfloat16*>(ep.out0)[off] = __float2bfloat16_rn(x);
+          if constexpr (kOut1) reinterpret_cast<__nv_bfloat16*>(ep.out1)[off] = __float2bfloat16_rn(sx);
+        }
+      }
+    }
+  }
+}
+// A/B on one B200 (C = 128 stage, 256 clips): activation-only epilogues -3..-4 %; the residual variants lose 15-25 %
+// (4-byte accesses keep a quarter of the bytes in flight per load instruction), so those stay on the transpose path.
+__device__ __forceinline__ bool epilogue_direct_supported(int variant) {
+  return variant == EV_SILU_BF16 || variant == EV_BF16;
+}
+
 
 // Transposed accumulator (conv_ts.cu): TMEM lanes = output channels, TMEM columns = time rows of a 256-row tile.
 // The 16 epilogue warps split the tile as (4 channel quarters) x (4 row quarters of 64); a warp's chunk is 32
@@ -328,6 +387,16 @@ __device__ __forceinline__ void epilogue_tile_transposed(const Epilogue& ep, int
     uint32_t acc[32];
     ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + r0, acc);
     ptx::tmem_ld_wait();
+    if (epilogue_direct_supported(variant)) {  // warp-uniform: no shared memory on this path
+      const int tfirst = t0 + r0;
+      const int nv = min(32, max(0, T - tfirst));
+      const int ch = q * 32 + lane;
+      const size_t o = ((size_t)clip * T + tfirst) * (size_t)ep.ldo + ch;
+      const float bch = ep.bias ? __ldg(ep.bias + ch) : 0.f;
+      if (variant == EV_SILU_BF16) epilogue_rows_direct<EV_SILU_BF16>(ep, acc, o, nv, bch);
+      else epilogue_rows_direct<EV_BF16>(ep, acc, o, nv, bch);
+      continue;
+    }
 #pragma unroll
     for (int i = 0; i < 32; ++i) stg[i * CW + lane] = __uint_as_float(acc[i]);
     __syncwarp();
