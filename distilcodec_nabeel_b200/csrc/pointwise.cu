@@ -492,7 +492,11 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
 int launch_gather_rows(const float* table, const int64_t* idx, int64_t nrows, int D, int64_t table_rows, float* o32,
                        __nv_bfloat16* o16, cudaStream_t st) {
   if (nrows == 0) return DC_OK;
-  ProfScope ps(PC_GATHER, 0, (double)nrows * D * (4.0 + (o32 ? 4.0 : 0.0) + (o16 ? 2.0 : 0.0)), st);
+  // compulsory bytes: a table row is read from HBM at most once per launch (repeats hit L2), outputs written once
+  ProfScope ps(PC_GATHER, 0,
+               (double)D * (4.0 * (double)(nrows < table_rows ? nrows : table_rows) +
+                            (double)nrows * ((o32 ? 4.0 : 0.0) + (o16 ? 2.0 : 0.0))),
+               st);
   gather_rows_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(table, idx, nrows, D, table_rows, o32, o16);
   ++g_launches_pw;
   DC_CUDA(cudaGetLastError());
