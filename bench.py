@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine tunable key=value (dc_set_option), repeatable")
+    ap.add_argument("--chunk", type=int, default=0, help="clips per device pass of the host-buffer (e2e) leg; 0 = Pipeline default")
     ap.add_argument("--cpu-clips", type=int, default=2, help="bounded CPU-baseline sample: clips of --cpu-seconds")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
@@ -205,7 +206,7 @@ def main():
     for kv in args.opt:
         k, v = kv.split("=")
         eng.set_option(k, float(v))
-    pipe = Pipeline(eng)
+    pipe = Pipeline(eng, chunk=args.chunk or None)
     # two alternating synthetic batches (bit-identical on every machine: numpy Philox), kept on host (pinned) and in HBM
     base = make_mel(8, T, seed=100 + rank)
     reps = (B + 7) // 8
