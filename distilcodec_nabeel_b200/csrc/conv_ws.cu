@@ -197,6 +197,24 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //                 fused epilogue (residual, dual store / 3-branch mean) -> global; it is the HBM latency chain of
 //                 the kernel, so it gets two tiles in flight, epilogue 1 (no global traffic) gets 4 warps
 constexpr int kPairE1Warps = 4, kPairE2Warps = 16;
+// Epilogue 2 is a memory-latency chain per tile (TMEM -> residual / mean operands from L2 or HBM -> stores; a
+// clock64 trace of one CTA showed ~4800 cycles per tile and group with the MMA thread stalling on d2empty): NG2 groups
+// of 16 / NG2 warps, one D2 accumulator each, keep NG2 tiles in flight.  A warp covers its TMEM lane quarter x all C
+// columns.
+#ifndef DC_PAIR_NG2
+#define DC_PAIR_NG2 4
+#endif
+constexpr int kPairNG2 = DC_PAIR_NG2, kPairG2Warps = kPairE2Warps / kPairNG2;
+static_assert(kPairNG2 == 2 || kPairNG2 == 4, "2 groups of 8 warps or 4 groups of 4");
+#ifdef DC_PAIR_TRACE  // experiment builds: per-role clock64 stamps of CTA 0, tiles 64..127 of its sequence
+__device__ long long g_pair_trace[16][64];
+#define PTRACE(ev, i) do { if (blockIdx.x == 0 && (i) >= 64 && (i) < 128) g_pair_trace[ev][(i) - 64] = clock64(); } while (0)
+extern "C" int dc_debug_pair_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_pair_trace, sizeof(g_pair_trace));
+}
+#else
+#define PTRACE(ev, i) do { } while (0)
+#endif
 constexpr int kPairThreads = 64 + 32 * (kPairE1Warps + kPairE2Warps);
 
 struct PairLayout {
@@ -226,7 +244,8 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     relative to the first output row*/, const float* __restrict__ bias1, Epilogue ep, int variant,
                     PairLayout lay, int tiles_per_clip, int total_tiles) {
   constexpr int SW = C * 2, PITCH = C * 2;
-  constexpr int TMEM_COLS = 4 * C;  // D1[2], D2[2]
+  constexpr int TMEM_COLS = (2 + kPairNG2) * C <= 128 ? 128 : ((2 + kPairNG2) * C <= 256 ? 256 : 512);  // D1[2], D2[NG2]
+  static_assert((2 + kPairNG2) * C <= 512, "TMEM");
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, C);
   constexpr int W_TAP_BYTES = C * C * 2;
   const int MO = 128 - (J - 1), p2 = (J - 1) / 2;
@@ -243,9 +262,9 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* d1empty = d1full + 2;                                      // [2]
   uint64_t* tfull = d1empty + 2;                                       // [2]  t tile written by epilogue 1
   uint64_t* tempty = tfull + 2;                                        // [2]  t tile consumed by conv2's MMAs
-  uint64_t* d2full = tempty + 2;                                       // [2]
-  uint64_t* d2empty = d2full + 2;                                      // [2]
-  uint64_t* wbar = d2empty + 2;                                        // [1]
+  uint64_t* d2full = tempty + 2;                                       // [NG2]
+  uint64_t* d2empty = d2full + kPairNG2;                               // [NG2]
+  uint64_t* wbar = d2empty + kPairNG2;                                 // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -268,8 +287,10 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         ptx::mbar_init(&d1empty[i], kPairE1Warps);
         ptx::mbar_init(&tfull[i], kPairE1Warps);
         ptx::mbar_init(&tempty[i], 1);
+      }
+      for (int i = 0; i < kPairNG2; ++i) {
         ptx::mbar_init(&d2full[i], 1);
-        ptx::mbar_init(&d2empty[i], 8);
+        ptx::mbar_init(&d2empty[i], kPairG2Warps);
       }
       ptx::mbar_init(wbar, 1);
       ptx::fence_barrier_init();
@@ -299,6 +320,7 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int clip = tile / tiles_per_clip, o0 = (tile % tiles_per_clip) * MO;
         ptx::mbar_wait(&aempty[stage], phase ^ 1);
+        PTRACE(14, (tile - (int)blockIdx.x) / (int)gridDim.x);
         ptx::mbar_expect_tx(&afull[stage], a_bytes);
         ptx::tma_load_3d(sA + stage * lay.a_stage_bytes, &tmA, &afull[stage], 0, o0 + shift_a, clip);
         if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -317,8 +339,11 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       auto conv1 = [&](int i) {
         const int b = i & 1;
+        PTRACE(0, i);
         ptx::mbar_wait(&d1empty[b], ((i >> 1) & 1) ^ 1);
+        PTRACE(1, i);
         ptx::mbar_wait(&afull[stage], phase);
+        PTRACE(2, i);
         ptx::tc_fence_after();
         uint64_t da = ptx::make_smem_desc<SW>(ptx::smem_u32(sA + stage * lay.a_stage_bytes));
         uint64_t dw = w1_desc;
@@ -334,12 +359,18 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         ptx::mma_commit(&aempty[stage]);
         ptx::mma_commit(&d1full[b]);
+        PTRACE(3, i);
         if (++stage == stages) { stage = 0; phase ^= 1; }
       };
       auto conv2 = [&](int i) {
-        const int b = i & 1;
-        ptx::mbar_wait(&d2empty[b], ((i >> 1) & 1) ^ 1);
+        const int b = i & 1;                         // t buffer
+        const int b2 = i % kPairNG2;                 // D2 accumulator / epilogue-2 group
+        const uint32_t ph2 = (uint32_t)(i / kPairNG2) & 1u;
+        PTRACE(4, i);
+        ptx::mbar_wait(&d2empty[b2], ph2 ^ 1);
+        PTRACE(5, i);
         ptx::mbar_wait(&tfull[b], (i >> 1) & 1);
+        PTRACE(6, i);
         ptx::tc_fence_after();
         uint64_t dt = ptx::make_smem_desc<SW>(ptx::smem_u32(sT + b * lay.t_bytes));
         uint64_t dw = w2_desc;
@@ -347,14 +378,15 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int j = 0; j < J; ++j) {  // conv2 tap j reads t rows r + j
 #pragma unroll
           for (int k = 0; k < C / 16; ++k) {
-            ptx::mma_bf16_ss(tm_d2 + b * C, dt + 2 * k, dw + 2 * k, IDESC, accum);
+            ptx::mma_bf16_ss(tm_d2 + b2 * C, dt + 2 * k, dw + 2 * k, IDESC, accum);
             accum = 1;
           }
           dt += t_step;
           dw += W_TAP_BYTES >> 4;
         }
         ptx::mma_commit(&tempty[b]);
-        ptx::mma_commit(&d2full[b]);
+        ptx::mma_commit(&d2full[b2]);
+        PTRACE(7, i);
       };
       if (n_my > 0) conv1(0);
       for (int i = 0; i < n_my; ++i) {
@@ -375,8 +407,10 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int gt = o0 - p2 + row;                      // sequence position of this t row
       const bool inside = gt >= 0 && gt < T;
       ptx::mbar_wait_sleepy(&d1full[b], (i >> 1) & 1);
+      if (warp == 2 && lane == 0) PTRACE(8, i);
       ptx::tc_fence_after();
       ptx::mbar_wait(&tempty[b], ((i >> 1) & 1) ^ 1);    // conv2 of tile i-2 has finished reading this t buffer
+      if (warp == 2 && lane == 0) PTRACE(9, i);
       uint8_t* trow = sT + b * lay.t_bytes + row * PITCH;
 #pragma unroll
       for (int c = 0; c < C / 32; ++c) {
@@ -404,26 +438,35 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) {
         ptx::mbar_arrive(&tfull[b]);
         ptx::mbar_arrive(&d1empty[b]);
+        if (warp == 2) PTRACE(10, i);
       }
     }
   } else {
     // ------------------------------------------------------------ epilogue 2: D2 -> fused epilogue -> global
     const int e2w = warp - (2 + kPairE1Warps);  // 0..15
-    const int group = e2w >> 3;
-    const int wg = 2 + (e2w & 7);               // 2..9 with wg % 4 == warp % 4 (TMEM lane quarter)
+    const int group = e2w / kPairG2Warps;
+    const int wg = 2 + (e2w % kPairG2Warps);    // warp id as epilogue_tile expects: wg % 4 == warp % 4 (TMEM lane quarter)
     float* stg = reinterpret_cast<float*>(smem + lay.stg_off) + e2w * (32 * 16);
     int i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
-      if ((i & 1) != group) continue;           // group g owns accumulator D2[g]
+      if (i % kPairNG2 != group) continue;      // group g owns accumulator D2[g]
       const int clip = tile / tiles_per_clip, o0 = (tile % tiles_per_clip) * MO;
-      const int b = i & 1;
-      epilogue_prefetch(ep, clip, T, o0 + (wg & 3) * 32, ((wg - 2) >> 2) * (C / 2), C / 2, lane, o0 + MO);
-      ptx::mbar_wait_sleepy(&d2full[b], (i >> 1) & 1);
+      const uint32_t ph2 = (uint32_t)(i / kPairNG2) & 1u;
+      if constexpr (kPairG2Warps == 8)
+        epilogue_prefetch(ep, clip, T, o0 + (wg & 3) * 32, ((wg - 2) >> 2) * (C / 2), C / 2, lane, o0 + MO);
+      else
+        epilogue_prefetch(ep, clip, T, o0 + (wg & 3) * 32, 0, C, lane, o0 + MO);
+      if (wg == 2 && lane == 0) PTRACE(11, i);
+      ptx::mbar_wait_sleepy(&d2full[group], ph2);
+      if (wg == 2 && lane == 0) PTRACE(12, i);
       ptx::tc_fence_after();
-      epilogue_tile<C, 16>(ep, variant, stg, tm_d2 + b * C, clip, o0, 0, T, wg, lane, o0 + MO);
+      epilogue_tile<C, 16>(ep, variant, stg, tm_d2 + group * C, clip, o0, 0, T, wg, lane, o0 + MO);
+      if constexpr (kPairG2Warps == 4)          // 4-warp groups: the same warp also takes the other column half
+        epilogue_tile<C, 16>(ep, variant, stg, tm_d2 + group * C, clip, o0, 0, T, wg + 4, lane, o0 + MO);
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&d2empty[b]);
+      if (lane == 0) ptx::mbar_arrive(&d2empty[group]);
+      if (wg == 2 && lane == 0) PTRACE(13, i);
     }
   }
 
