@@ -182,6 +182,13 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // brings 128 + (J-1)*dil rows and all J taps read it through row-shifted descriptors, so the L2 -> SM operand
 // traffic of a k = 11 conv drops 29 % (528 -> 375 KB per tile and chunk).  128 x 256 tiles, two TMEM accumulators,
 // weights stream through a 4-stage ring of 32 KB (tap, chunk) tiles, activations through 2 chunk buffers.
+#ifdef DC_TSW_TRACE  // experiment builds: clock64 stamps of CTA 0, tiles 16..79 of its sequence (last launch wins)
+__device__ long long g_tsw_trace[12][64];
+#define TTRACE(ev, i) do { if (blockIdx.x == 0 && (i) >= 16 && (i) < 80) g_tsw_trace[ev][(i) - 16] = clock64(); } while (0)
+extern "C" int dc_debug_tsw_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_tsw_trace, sizeof(g_tsw_trace)); }
+#else
+#define TTRACE(ev, i) do { } while (0)
+#endif
 namespace tsw {
 constexpr int BN = 256, BK = 64;
 constexpr int A_ROWS = 184;                       // 128 + max halo (50), multiple of 8
@@ -286,15 +293,30 @@ conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t tap_step = (uint32_t)(s.dil * BK * 2) >> 4;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int p = it & 1;
+        TTRACE(0, it);
         ptx::mbar_wait(&tempty[p], ((it >> 1) & 1) ^ 1);
+        TTRACE(1, it);
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + p * BN;
+        long long wa = 0, wb = 0;
         for (int kc = 0; kc < kchunks; ++kc) {
+#ifdef DC_TSW_TRACE
+          long long c0 = clock64();
+#endif
           ptx::mbar_wait(&afull[as], aphase);
+#ifdef DC_TSW_TRACE
+          wa += clock64() - c0;
+#endif
           ptx::tc_fence_after();
           uint64_t da = ptx::make_smem_desc<128>(ptx::smem_u32(sA + as * A_BYTES));
           for (int j = 0; j < s.J; ++j) {
+#ifdef DC_TSW_TRACE
+            long long c1 = clock64();
+#endif
             ptx::mbar_wait(&bfull[bs], bphase);
+#ifdef DC_TSW_TRACE
+            wb += clock64() - c1;
+#endif
             ptx::tc_fence_after();
             const uint64_t db = ptx::make_smem_desc<128>(ptx::smem_u32(sB + bs * B_BYTES));
             const uint32_t acc = (kc | j) != 0 ? 1u : 0u;
@@ -308,6 +330,10 @@ conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (++as == A_STAGES) { as = 0; aphase ^= 1; }
         }
         ptx::mma_commit(&tfull[p]);
+        TTRACE(2, it);
+#ifdef DC_TSW_TRACE
+        if (blockIdx.x == 0 && it >= 16 && it < 80) { g_tsw_trace[3][it - 16] = wa; g_tsw_trace[4][it - 16] = wb; }
+#endif
       }
     }
   } else {
@@ -322,12 +348,15 @@ conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int clip = m_blk / tiles_per_clip, t0 = (m_blk % tiles_per_clip) * 128;
       const int p = it & 1;
       epilogue_prefetch(ep, clip, s.T, t0 + (wg & 3) * 32, n0 + ((wg - 2) >> 2) * (BN / 2), BN / 2, lane);
+      if (wg == 2 && lane == 0) TTRACE(5, it);
       ptx::mbar_wait_sleepy(&tfull[p], (it >> 1) & 1);
+      if (wg == 2 && lane == 0) TTRACE(6, it);
       ptx::tc_fence_after();
       epilogue_tile<BN, CW>(ep, variant, stg, tmem_base + p * BN, clip, t0, n0, s.T, wg, lane);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[p]);
+      if (wg == 2 && lane == 0) TTRACE(7, it);
     }
   }
 
