@@ -26,23 +26,44 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
 static thread_local uint64_t g_launches_ts = 0;
 uint64_t conv_ts_launch_count() { return g_launches_ts; }
 
+#ifdef DC_TSW_TRACE  // experiment builds: clock64 stamps of CTA 0, tiles 16..79 of its sequence (last launch wins)
+__device__ long long g_tsw_trace[12][64];
+#define TTRACE(ev, i) do { if (blockIdx.x == 0 && (i) >= 16 && (i) < 80) g_tsw_trace[ev][(i) - 16] = clock64(); } while (0)
+extern "C" int dc_debug_tsw_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_tsw_trace, sizeof(g_tsw_trace)); }
+#else
+#define TTRACE(ev, i) do { } while (0)
+#endif
 namespace ts {
 constexpr int C = 128, N = 128, BK = 64, KCH = C / BK;  // two 64-channel chunks
-constexpr int BOX_ROWS = 160, A_ROWS = 2 * BOX_ROWS;    // 320 >= 256 + max halo (56)
-constexpr int A_BYTES = A_ROWS * BK * 2;                // 40 KB per chunk buffer
 constexpr int B_BYTES = N * BK * 2;                     // 16 KB per (tap, chunk) weight tile
-constexpr int B_STAGES = 5;
 constexpr int STG_BYTES = 16 * 32 * 32 * 4;             // 16 epilogue warps x (32 rows x 32 fp32)
-constexpr int A_OFF = 0, B_OFF = KCH * A_BYTES, STG_OFF = B_OFF + B_STAGES * B_BYTES, BAR_OFF = STG_OFF + STG_BYTES;
-constexpr int TOTAL = BAR_OFF + 256 + 1024;
 constexpr int THREADS = 64 + 16 * 32;
-static_assert(TOTAL <= 232448, "shared memory budget");
+// <BOXR, AST, BST>: rows per activation TMA box (two boxes per 64-channel chunk buffer), chunk buffers, weight stages.
+//   <160, 2, 5>: any halo up to 64 rows (k = 11, dilation 5).
+//   <136, 3, 3>: k = 3 (halo <= 16 rows): a third, smaller activation buffer, loaded one chunk ahead of the weight
+//   tiles.  A clock64 trace (scripts/tsw_trace.py) shows the k = 3 layers' MMA thread waiting ~3500 cycles per tile on
+//   the activation barrier (7100 cycles per 256-row tile against 3072 of MMA time, at any clock); this variant is
+//   worth 2-3 % only, and halving the loaded bytes (a timing experiment) 8 %: the wait is not the load itself.  Open.
+template <int BOXR, int AST, int BST>
+struct Cfg {
+  static constexpr int A_ROWS = 2 * BOXR;
+  static constexpr int A_BYTES = A_ROWS * BK * 2;
+  static_assert(A_BYTES % 1024 == 0, "swizzled tiles need 1024-byte aligned bases");
+  static constexpr int A_OFF = 0, B_OFF = AST * A_BYTES, STG_OFF = B_OFF + BST * B_BYTES, BAR_OFF = STG_OFF + STG_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static_assert(TOTAL <= 232448, "shared memory budget");
+};
+constexpr int MAX_A_ROWS = 320;
 }  // namespace ts
 
+template <int BOXR, int AST, int BST>
 __global__ void __launch_bounds__(ts::THREADS, 1)
 conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvGemmShape s,
                Epilogue ep, int variant, int tiles_per_clip, int total_tiles) {
   using namespace ts;
+  using L = Cfg<BOXR, AST, BST>;
+  constexpr int BOX_ROWS = BOXR, A_BYTES = L::A_BYTES, B_STAGES = BST, A_STAGES = AST;
+  constexpr int A_OFF = L::A_OFF, B_OFF = L::B_OFF, STG_OFF = L::STG_OFF, BAR_OFF = L::BAR_OFF;
   // Operand roles are swapped: the WEIGHT tile (128 output channels x 64) is the MMA's A operand (M = 128) and the
   // 256 activation rows are its B operand (N = 256), so the accumulator is transposed (TMEM lane = channel, column
   // = time row).  An M = 128, N = 128 MMA reads 8 KB of shared memory per 64 tensor cycles = the full 128 B/clk of
@@ -52,9 +73,9 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem + A_OFF;
   uint8_t* sB = smem + B_OFF;
-  uint64_t* afull = reinterpret_cast<uint64_t*>(smem + BAR_OFF);  // [KCH]
-  uint64_t* aempty = afull + KCH;                                  // [KCH]
-  uint64_t* bfull = aempty + KCH;                                  // [B_STAGES]
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem + BAR_OFF);  // [A_STAGES]
+  uint64_t* aempty = afull + A_STAGES;                             // [A_STAGES]
+  uint64_t* bfull = aempty + A_STAGES;                             // [B_STAGES]
   uint64_t* bempty = bfull + B_STAGES;                             // [B_STAGES]
   uint64_t* tfull = bempty + B_STAGES;                             // [2]
   uint64_t* tempty = tfull + 2;                                    // [2]
@@ -69,7 +90,7 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < KCH; ++i) {
+      for (int i = 0; i < A_STAGES; ++i) {
         ptx::mbar_init(&afull[i], 1);
         ptx::mbar_init(&aempty[i], 1);
       }
@@ -94,43 +115,67 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (same order as the MMA issuer consumes)
     if (ptx::elect_one()) {  // one lane, known to the compiler: operands go to uniform registers
-      int bs = 0;
+      // One thread issues both operand streams.  The weight ring is the back-pressure path (its stages free only as
+      // MMAs complete), so an activation load issued AFTER a chunk's weight loads starts a whole chunk late; with a
+      // third activation buffer the load of chunk c + 1 is issued BEFORE the weight tiles of chunk c.
+      constexpr int AHEAD = A_STAGES >= 3 ? 1 : 0;
+      int bs = 0, as = 0;
       uint32_t bphase = 0, aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int n_chunks = my_tiles * KCH;
+      auto load_a = [&](int c) {  // chunk c of this CTA's sequence = (tile c / KCH, channel chunk c % KCH)
+        const int tile = blockIdx.x + (c / KCH) * gridDim.x, kc = c % KCH;
         const int clip = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * 256;
-        for (int kc = 0; kc < KCH; ++kc) {
-          ptx::mbar_wait(&aempty[kc], aphase ^ 1);
-          ptx::mbar_expect_tx(&afull[kc], A_BYTES);
-          ptx::tma_load_3d(sA + kc * A_BYTES, &tmA, &afull[kc], kc * BK, t0 + s.shift0, clip);
-          ptx::tma_load_3d(sA + kc * A_BYTES + BOX_ROWS * BK * 2, &tmA, &afull[kc], kc * BK, t0 + s.shift0 + BOX_ROWS,
-                           clip);
-          for (int j = 0; j < s.J; ++j) {
-            ptx::mbar_wait(&bempty[bs], bphase ^ 1);
-            ptx::mbar_expect_tx(&bfull[bs], B_BYTES);
-            ptx::tma_load_2d(sB + bs * B_BYTES, &tmW, &bfull[bs], j * C + kc * BK, 0);
-            if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
-          }
+        ptx::mbar_wait(&aempty[as], aphase ^ 1);
+        ptx::mbar_expect_tx(&afull[as], A_BYTES);
+        ptx::tma_load_3d(sA + as * A_BYTES, &tmA, &afull[as], kc * BK, t0 + s.shift0, clip);
+        ptx::tma_load_3d(sA + as * A_BYTES + BOX_ROWS * BK * 2, &tmA, &afull[as], kc * BK, t0 + s.shift0 + BOX_ROWS, clip);
+        if (++as == A_STAGES) { as = 0; aphase ^= 1; }
+      };
+      for (int c = 0; c < AHEAD && c < n_chunks; ++c) load_a(c);
+      for (int c = 0; c < n_chunks; ++c) {
+        if (c + AHEAD < n_chunks) load_a(c + AHEAD);
+        const int kc = c % KCH;
+        for (int j = 0; j < s.J; ++j) {
+          ptx::mbar_wait(&bempty[bs], bphase ^ 1);
+          ptx::mbar_expect_tx(&bfull[bs], B_BYTES);
+          ptx::tma_load_2d(sB + bs * B_BYTES, &tmW, &bfull[bs], j * C + kc * BK, 0);
+          if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
         }
-        aphase ^= 1;
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (single thread)
     if (ptx::elect_one()) {  // one lane, known to the compiler: operands go to uniform registers
-      int bs = 0, it = 0;
+      int bs = 0, as = 0, it = 0;
       uint32_t bphase = 0, aphase = 0;
       const uint32_t tap_step = (uint32_t)(s.dil * BK * 2) >> 4;   // descriptor start-address units (16 B) per tap
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int p = it & 1;
+        TTRACE(0, it);
         ptx::mbar_wait(&tempty[p], ((it >> 1) & 1) ^ 1);
+        TTRACE(1, it);
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + p * 256;
+        long long wa = 0, wb = 0;
         for (int kc = 0; kc < KCH; ++kc) {
-          ptx::mbar_wait(&afull[kc], aphase);
+#ifdef DC_TSW_TRACE
+          long long c0 = clock64();
+#endif
+          ptx::mbar_wait(&afull[as], aphase);
+#ifdef DC_TSW_TRACE
+          wa += clock64() - c0;
+#endif
           ptx::tc_fence_after();
-          uint64_t da = ptx::make_smem_desc<128>(ptx::smem_u32(sA + kc * A_BYTES));
+          uint64_t da = ptx::make_smem_desc<128>(ptx::smem_u32(sA + as * A_BYTES));
           for (int j = 0; j < s.J; ++j) {
+#ifdef DC_TSW_TRACE
+            long long c1 = clock64();
+#endif
             ptx::mbar_wait(&bfull[bs], bphase);
+#ifdef DC_TSW_TRACE
+            wb += clock64() - c1;
+#endif
             ptx::tc_fence_after();
             const uint64_t db = ptx::make_smem_desc<128>(ptx::smem_u32(sB + bs * B_BYTES));
             const uint32_t acc = (kc | j) != 0 ? 1u : 0u;
@@ -141,10 +186,14 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
             da += tap_step;  // tap j + 1 = the same rows, dil rows further down
           }
-          ptx::mma_commit(&aempty[kc]);
+          ptx::mma_commit(&aempty[as]);
+          if (++as == A_STAGES) { as = 0; aphase ^= 1; }
         }
         ptx::mma_commit(&tfull[p]);
-        aphase ^= 1;
+        TTRACE(2, it);
+#ifdef DC_TSW_TRACE
+        if (blockIdx.x == 0 && it >= 16 && it < 80) { g_tsw_trace[3][it - 16] = wa; g_tsw_trace[4][it - 16] = wb; }
+#endif
       }
     }
   } else {
@@ -159,12 +208,15 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // this warp's region: 32 channels (one 128-byte line per row) x 64 rows
       epilogue_prefetch(ep, clip, s.T, t0 + (warp16 >> 2) * 64, (warp16 & 3) * 32, 32, lane);
       epilogue_prefetch(ep, clip, s.T, t0 + (warp16 >> 2) * 64 + 32, (warp16 & 3) * 32, 32, lane);
+      if (warp16 == 0 && lane == 0) TTRACE(5, it);
       ptx::mbar_wait_sleepy(&tfull[p], (it >> 1) & 1);
+      if (warp16 == 0 && lane == 0) TTRACE(6, it);
       ptx::tc_fence_after();
       epilogue_tile_transposed(ep, variant, stg, tmem_base + p * 256, clip, t0, s.T, warp16, lane);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[p]);
+      if (warp16 == 0 && lane == 0) TTRACE(7, it);
     }
   }
 
@@ -182,13 +234,6 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // brings 128 + (J-1)*dil rows and all J taps read it through row-shifted descriptors, so the L2 -> SM operand
 // traffic of a k = 11 conv drops 29 % (528 -> 375 KB per tile and chunk).  128 x 256 tiles, two TMEM accumulators,
 // weights stream through a 4-stage ring of 32 KB (tap, chunk) tiles, activations through 2 chunk buffers.
-#ifdef DC_TSW_TRACE  // experiment builds: clock64 stamps of CTA 0, tiles 16..79 of its sequence (last launch wins)
-__device__ long long g_tsw_trace[12][64];
-#define TTRACE(ev, i) do { if (blockIdx.x == 0 && (i) >= 16 && (i) < 80) g_tsw_trace[ev][(i) - 16] = clock64(); } while (0)
-extern "C" int dc_debug_tsw_trace(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_tsw_trace, sizeof(g_tsw_trace)); }
-#else
-#define TTRACE(ev, i) do { } while (0)
-#endif
 namespace tsw {
 constexpr int BN = 256, BK = 64;
 constexpr int A_ROWS = 184;                       // 128 + max halo (50), multiple of 8
@@ -438,18 +483,20 @@ int launch_conv_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGe
 }
 
 bool conv_ts_supported(const ConvGemmShape& s) {
-  return s.C == ts::C && s.N == ts::N && 256 + (s.J - 1) * s.dil <= ts::A_ROWS && s.J >= 1;
+  return s.C == ts::C && s.N == ts::N && 256 + (s.J - 1) * s.dil <= ts::MAX_A_ROWS && s.J >= 1;
 }
 
-int launch_conv_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
-                   cudaStream_t st, int sm_count) {
+template <int BOXR, int AST, int BST>
+static int launch_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
+                     cudaStream_t st, int sm_count) {
   using namespace ts;
-  DC_CHECK(conv_ts_supported(s), DC_ERR_SHAPE, "conv_ts: unsupported shape C=%d N=%d J=%d dil=%d", s.C, s.N, s.J, s.dil);
+  constexpr int BOX_ROWS = BOXR, TOTAL = Cfg<BOXR, AST, BST>::TOTAL;
+  DC_CHECK(256 + (s.J - 1) * s.dil <= 2 * BOXR, DC_ERR_SHAPE, "conv_ts: halo does not fit the activation buffer");
   static int attr_dev_mask = 0;
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
   if (!(attr_dev_mask & (1 << dev))) {
-    DC_CUDA(cudaFuncSetAttribute(conv_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
+    DC_CUDA(cudaFuncSetAttribute(conv_ts_kernel<BOXR, AST, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
     attr_dev_mask |= 1 << dev;
   }
   const int tiles_per_clip = (s.T + 255) / 256;
@@ -478,12 +525,21 @@ int launch_conv_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGem
     const double out_bytes = (e.out0 ? (e.out0_dt == DT_F32 ? 4.0 : 2.0) : 0.0) + (e.out1 ? 2.0 : 0.0) +
                              (e.res ? 4.0 : 0.0) + (e.add1 ? 8.0 : 0.0);
     ProfScope ps(PC_CONV_TS, 2.0 * macs, rows * C * 2.0 + (double)N * s.J * C * 2.0 + rows * N * out_bytes, st,
-                 "|C%d N%d J%d d%d e%d", C, N, s.J, s.dil, esig);
-    conv_ts_kernel<<<grid, THREADS, TOTAL, st>>>(tmA, tmW, s, e, epilogue_variant(e), tiles_per_clip, (int)total);
+                 AST == 2 ? "|C%d N%d J%d d%d e%d" : "<a3>|C%d N%d J%d d%d e%d", C, N, s.J, s.dil, esig);
+    conv_ts_kernel<BOXR, AST, BST><<<grid, THREADS, TOTAL, st>>>(tmA, tmW, s, e, epilogue_variant(e), tiles_per_clip, (int)total);
   }
   ++g_launches_ts;
   DC_CUDA(cudaGetLastError());
   return DC_OK;
+}
+
+int launch_conv_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
+                   cudaStream_t st, int sm_count) {
+  DC_CHECK(conv_ts_supported(s), DC_ERR_SHAPE, "conv_ts: unsupported shape C=%d N=%d J=%d dil=%d", s.C, s.N, s.J, s.dil);
+#ifndef DC_TS_NO_A3
+  if (s.J <= 3 && (s.J - 1) * s.dil <= 16) return launch_ts<136, 3, 3>(A, W, s, e, st, sm_count);
+#endif
+  return launch_ts<160, 2, 5>(A, W, s, e, st, sm_count);
 }
 
 }  // namespace dc

@@ -12,13 +12,14 @@ from distilcodec_nabeel_b200 import Engine
 from distilcodec_nabeel_b200 import random_init as weights
 
 Cc, N, J, dil, res = (int(v) for v in sys.argv[1:6])
+act = int(sys.argv[6]) if len(sys.argv) > 6 else 0      # 2 = SiLU (conv1-type epilogue when res = 0)
 eng = Engine(weights.make_state_dict("W0"), 0, "bf16")
-B, T = 64, 937 * (32 if Cc == 256 else 8)
+B, T = 64, 937 * {128: 64, 256: 32}.get(Cc, 8)
 a = torch.randn(B, T, Cc, device="cuda")
 w = torch.randn(N, J * Cc, device="cuda") * 0.02
 r = torch.randn(B, T, N, device="cuda") if res else None
 for _ in range(2):
-    eng.op_conv_gemm(a, w, None, r, -dil * (J - 1) // 2, dil, 0)
+    eng.op_conv_gemm(a, w, None, r, -dil * (J - 1) // 2, dil, act)
 torch.cuda.synchronize()
 lib = C.CDLL(os.environ["DC_LIB"])
 buf = (C.c_longlong * (12 * 64))()
