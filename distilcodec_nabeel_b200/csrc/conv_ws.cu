@@ -193,9 +193,9 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   warps 2..5    epilogue 1: D1 (TMEM) -> +b1 -> SiLU -> bf16 -> the t tile in shared memory, written directly in
 //                 the UMMA K-major swizzled layout (128B/64B swizzle = XOR of the 16-byte chunk index with the row
 //                 bits) and zeroed outside [0, T) (conv2's zero padding applies to t); fence.proxy.async; arrive
-//   warps 6..21   epilogue 2, two groups of 8 warps on alternate tiles (group g owns accumulator D2[g]): the usual
+//   warps 6..21   epilogue 2, four groups of 4 warps, one tile in four each (group g owns accumulator D2[g]): the usual
 //                 fused epilogue (residual, dual store / 3-branch mean) -> global; it is the HBM latency chain of
-//                 the kernel, so it gets two tiles in flight, epilogue 1 (no global traffic) gets 4 warps
+//                 the kernel, so it gets four tiles in flight, epilogue 1 (no global traffic) gets 4 warps
 constexpr int kPairE1Warps = 4, kPairE2Warps = 16;
 // Epilogue 2 is a memory-latency chain per tile (TMEM -> residual / mean operands from L2 or HBM -> stores; a
 // clock64 trace of one CTA showed ~4800 cycles per tile and group with the MMA thread stalling on d2empty): NG2 groups
