@@ -208,7 +208,11 @@ constexpr int kPairNG2 = DC_PAIR_NG2, kPairG2Warps = kPairE2Warps / kPairNG2;
 static_assert(kPairNG2 == 2 || kPairNG2 == 4, "2 groups of 8 warps or 4 groups of 4");
 #ifdef DC_PAIR_TRACE  // experiment builds: per-role clock64 stamps of CTA 0, tiles 64..127 of its sequence
 __device__ long long g_pair_trace[16][64];
-#define PTRACE(ev, i) do { if (blockIdx.x == 0 && (i) >= 64 && (i) < 128) g_pair_trace[ev][(i) - 64] = clock64(); } while (0)
+#ifndef DC_PAIR_TRACE_C   // which launches record: -DDC_PAIR_TRACE_C=64 -DDC_PAIR_TRACE_J=7 (dilation 1); the last one wins
+#define DC_PAIR_TRACE_C 32
+#define DC_PAIR_TRACE_J 11
+#endif
+#define PTRACE(ev, i) do { if (blockIdx.x == 0 && C == DC_PAIR_TRACE_C && J == DC_PAIR_TRACE_J && (i) >= 64 && (i) < 128) g_pair_trace[ev][(i) - 64] = clock64(); } while (0)
 extern "C" int dc_debug_pair_trace(long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_pair_trace, sizeof(g_pair_trace));
 }
