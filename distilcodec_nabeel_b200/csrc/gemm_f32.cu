@@ -4,7 +4,8 @@
 // (models/encoders.py:23-37, convnext_utils.py:250-255, grfvq.py:68-96, residual_vq.py:61-62,
 //  generators.py:50-114, convnext_utils.py:36-102).
 // 128 x BN output tile per 256-thread block, 8 x (BN/16) outputs per thread, BK = 16, register-prefetched
-// double buffering through shared memory.
+// double buffering through shared memory.  BN = 128 (8 x 8 per thread, packed FFMA2: 32 issue slots per 64 FMAs) where
+// N allows; the narrow layers use BN = 64 / 32.  Accumulation order per output is k-ascending in every variant.
 #include "common.cuh"
 
 namespace dc {
@@ -36,13 +37,14 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
   const int kchunks = s.C / BK;
   const int total = s.J * kchunks;
 
-  float acc[TM][TN];
+  float2 acc[TM][TN / 2];  // column pairs: one packed FMA (fma.rn.f32x2) per pair, same IEEE result as two scalar FMAs
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN / 2; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
-  float4 ra0, ra1, rb;
+  constexpr bool B2 = BN == 128;  // 32 threads cover a B row: each thread loads rows b_k and b_k + 8
+  float4 ra0, ra1, rb, rb2;
   auto load_regs = [&](int it) {
     const int j = it / kchunks, c0 = (it % kchunks) * BK;
     const int t = t0 + a_r + s.shift0 + j * s.dil;
@@ -56,11 +58,13 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
     }
     if (b_active)
       rb = __ldg(reinterpret_cast<const float4*>(W + (size_t)(j * s.C + c0 + b_k) * s.N + n0 + b_n));
+    if constexpr (B2) rb2 = __ldg(reinterpret_cast<const float4*>(W + (size_t)(j * s.C + c0 + b_k + 8) * s.N + n0 + b_n));
   };
   auto store_smem = [&](int buf) {
     As[buf][a_k + 0][a_r] = ra0.x; As[buf][a_k + 1][a_r] = ra0.y; As[buf][a_k + 2][a_r] = ra0.z; As[buf][a_k + 3][a_r] = ra0.w;
     As[buf][a_k + 4][a_r] = ra1.x; As[buf][a_k + 5][a_r] = ra1.y; As[buf][a_k + 6][a_r] = ra1.z; As[buf][a_k + 7][a_r] = ra1.w;
     if (b_active) *reinterpret_cast<float4*>(&Bs[buf][b_k][b_n]) = rb;
+    if constexpr (B2) *reinterpret_cast<float4*>(&Bs[buf][b_k + 8][b_n]) = rb2;
   };
 
   load_regs(0);
@@ -75,12 +79,22 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
       const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * TM]);
       const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * TM + 4]);
       a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      if constexpr (TN >= 4) {
 #pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = Bs[buf][kk][tx * TN + j];
+        for (int j = 0; j < TN; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * TN + j]);
+          b[j] = bv.x; b[j + 1] = bv.y; b[j + 2] = bv.z; b[j + 3] = bv.w;
+        }
+      } else {
+        const float2 bv = *reinterpret_cast<const float2*>(&Bs[buf][kk][tx * TN]);
+        b[0] = bv.x; b[1] = bv.y;
+      }
 #pragma unroll
-      for (int i = 0; i < TM; ++i)
+      for (int i = 0; i < TM; ++i) {
+        const float2 ai = make_float2(a[i], a[i]);
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN / 2; ++j) acc[i][j] = ffma2(ai, make_float2(b[2 * j], b[2 * j + 1]), acc[i][j]);
+      }
     }
     if (it + 1 < total) store_smem(buf ^ 1);
     __syncthreads();
@@ -92,7 +106,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
     if (t >= s.T) continue;
     const size_t row = (size_t)clip * s.T + t;
 #pragma unroll
-    for (int j = 0; j < TN; ++j) epilogue_store(ep, row, n0 + tx * TN + j, acc[i][j]);
+    for (int j = 0; j < TN; ++j) epilogue_store(ep, row, n0 + tx * TN + j, (j & 1) ? acc[i][j / 2].y : acc[i][j / 2].x);
   }
 }
 
@@ -110,6 +124,12 @@ int launch_gemm_f32(const float* A, const float* W, const ConvGemmShape& s_in, c
   const double rows = (double)s.B * s.T;
   ProfScope ps(PC_GEMM_F32, 2.0 * rows * s.N * s.J * s.C * s.alg_scale,
                rows * s.C * 4.0 + (double)s.N * s.J * s.C * 4.0 + rows * s.N * 4.0, st);
+#ifndef DC_F32_NO_BN128
+  if (s.N % 128 == 0) {
+    dim3 grid((unsigned)mt, s.N / 128);
+    gemm_f32_kernel<128><<<grid, 256, 0, st>>>(A, W, s, e, tiles_per_clip);
+  } else
+#endif
   if (s.N % 64 == 0) {
     dim3 grid((unsigned)mt, s.N / 64);
     gemm_f32_kernel<64><<<grid, 256, 0, st>>>(A, W, s, e, tiles_per_clip);
