@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
       a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
       if constexpr (TN >= 4) {
 #pragma unroll
-        for (int j = 0; j < TN; j += 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * TN + j]);
+        for (int j = 0; j < TN; j += 4) {  // column groups of 4 at a stride of 64: conflict-free LDS.128 (16 B per lane)
+          const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][kk][(j / 4) * 64 + tx * 4]);
           b[j] = bv.x; b[j + 1] = bv.y; b[j + 2] = bv.z; b[j + 3] = bv.w;
         }
       } else {
@@ -106,7 +106,10 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
     if (t >= s.T) continue;
     const size_t row = (size_t)clip * s.T + t;
 #pragma unroll
-    for (int j = 0; j < TN; ++j) epilogue_store(ep, row, n0 + tx * TN + j, (j & 1) ? acc[i][j / 2].y : acc[i][j / 2].x);
+    for (int j = 0; j < TN; ++j) {
+      const int col = TN >= 4 ? (j / 4) * 64 + tx * 4 + (j & 3) : tx * TN + j;  // the column this accumulator belongs to
+      epilogue_store(ep, row, n0 + col, (j & 1) ? acc[i][j / 2].y : acc[i][j / 2].x);
+    }
   }
 }
 
