@@ -86,3 +86,32 @@ def test_time_tiles_cover_the_clip_in_order():
             assert (lo == 0 or s - lo == halo) and (hi == T or hi - e == halo)
             if nxt:
                 assert nxt[2] == e
+
+
+def test_partition_and_tiles_properties_hypothesis():
+    """Property tests (hypothesis): shards are contiguous, balanced and cover [0, n); time tiles cover [0, T) once,
+    in order, with halos clipped at the clip ends only."""
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    from distilcodec_nabeel_b200.sharding import shard_clips, shard_sizes, time_tiles
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 5000), st.integers(1, 64))
+    def shards(n, ws):
+        parts = [shard_clips(n, ws, r) for r in range(ws)]
+        assert [i for p in parts for i in p] == list(range(n))
+        sizes = [len(p) for p in parts]
+        assert sizes == shard_sizes(n, ws) and max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 100000), st.integers(1, 20000), st.integers(0, 300))
+    def tiles(T, tile, halo):
+        ts = time_tiles(T, tile, halo)
+        assert [x for (_, _, s, e) in ts for x in (s, e)][0] == 0 and ts[-1][3] == T
+        assert all(a[3] == b[2] for a, b in zip(ts, ts[1:]))
+        for lo, hi, s, e in ts:
+            assert lo == max(0, s - halo) and hi == min(T, e + halo) and 0 < e - s <= tile
+
+    shards()
+    tiles()
