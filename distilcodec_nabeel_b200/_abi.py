@@ -51,6 +51,7 @@ SIGNATURES = {
     "dc_quantizer_decode": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "dc_generator_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "dc_mel_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "dc_copy2d_async": (_i, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
     "dc_ncl_to_nlc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "dc_nlc_to_ncl": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "dc_op_conv_gemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

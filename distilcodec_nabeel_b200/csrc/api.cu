@@ -180,6 +180,35 @@ struct dc_handle_s {
 
 namespace dc {
 
+// forget every pointer into packed weights (the owner list has been freed); forwards fail with DC_ERR_STATE until
+// the next successful dc_finalize
+static void reset_packed(dc_handle_s* h) {
+  h->finalized = false;
+  h->stem = Dense();
+  h->stem_ln_w = h->stem_ln_b = h->final_ln_w = h->final_ln_b = nullptr;
+  for (int s = 0; s < 4; ++s) {
+    h->down_ln_w[s] = h->down_ln_b[s] = nullptr;
+    h->down_conv[s] = Dense();
+    h->enc_blocks[s].clear();
+  }
+  h->q_down = h->proj_in = h->proj_out = h->q_up = Dense();
+  h->q_down_blk = h->q_up_blk = Block();
+  h->codebook = nullptr;
+  h->codebook_bf16 = nullptr;
+  h->c2 = h->c2max = nullptr;
+  h->K = h->CD = 0;
+  h->mel_fb = h->mel_window = nullptr;
+  h->mel_twiddle = nullptr;
+  h->conv_pre = Dense();
+  for (auto& u : h->ups) u = Dense();
+  for (auto& a : h->rb)
+    for (auto& b : a)
+      for (auto& c : b)
+        for (auto& d : c) d = Dense();
+  h->post_w = nullptr;
+  h->post_C = 0;
+}
+
 static int run_dense(const dc_handle_s* h, const struct Dense& d, const void* A, int B, int T, Epilogue ep, cudaStream_t st);
 static int act_dt(const dc_handle_s* h) { return h->mode == DC_MODE_BF16 ? DT_BF16 : DT_F32; }
 static size_t act_es(const dc_handle_s* h) { return h->mode == DC_MODE_BF16 ? 2 : 4; }
@@ -613,9 +642,27 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
 }  // namespace dc
 
 // ================================================================================================ C ABI
+// Every entry point runs on the handle's device and puts the caller's current device back on exit (a host thread that
+// drives several GPUs, or a handle destroyed by a garbage collector, must not find its current device changed).
+struct DeviceGuard {
+  int prev = -1;
+  int enter(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev == device) {
+      prev = -1;
+      return DC_OK;
+    }
+    DC_CUDA(cudaSetDevice(device));
+    return DC_OK;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
 #define DC_API_BEGIN(h)                                                    \
   DC_CHECK((h) != nullptr, DC_ERR_ARG, "null handle");                     \
-  DC_CUDA(cudaSetDevice((h)->device))
+  DeviceGuard _dev_guard;                                                  \
+  DC_TRY(_dev_guard.enter((h)->device))
 #define DC_NEED_FINAL(h) DC_CHECK((h)->finalized, DC_ERR_STATE, "call dc_finalize() first")
 
 extern "C" {
@@ -661,7 +708,6 @@ int dc_create(int device, int mode, const dc_config* cfg, dc_handle* out) {
   DC_CUDA(cudaGetDeviceProperties(&prop, device));
   DC_CHECK(prop.major == 10, DC_ERR_ARCH, "device %d is sm_%d%d; this library contains only sm_100a code", device,
            prop.major, prop.minor);
-  DC_CUDA(cudaSetDevice(device));
   dc_handle_s* h = new dc_handle_s();
   h->device = device;
   h->mode = mode;
@@ -683,7 +729,8 @@ int dc_create(int device, int mode, const dc_config* cfg, dc_handle* out) {
 
 int dc_destroy(dc_handle h) {
   if (!h) return DC_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard;
+  guard.enter(h->device);
   cudaDeviceSynchronize();
   for (auto& kv : h->raw)
     if (kv.second.owned && kv.second.d) cudaFree(kv.second.d);
@@ -748,8 +795,12 @@ int dc_set_tensor(dc_handle h, const char* name, const float* data_dev, const in
 int dc_finalize(dc_handle h, void* stream) {
   DC_API_BEGIN(h);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // A handle that fails below (e.g. a second dc_finalize without the full state_dict: the raw matrices were dropped
+  // by the first one) must not keep pointers into the packed weights freed here: back to the empty state first.
+  DC_CUDA(cudaDeviceSynchronize());
   for (void* p : h->owned) cudaFree(p);
   h->owned.clear();
+  reset_packed(h);
   const dc_config& c = h->cfg;
   char buf[256];
   const bool has_enc = find_raw(h, "encoder.norm.weight") != nullptr;
@@ -1032,6 +1083,15 @@ int dc_mel_forward(dc_handle h, const float* audio_dev, int B, int Ls, float* me
   DC_CHECK(audio_dev && mel_ncl_dev && B > 0 && Ls > 0, DC_ERR_ARG, "bad argument to dc_mel_forward");
   return launch_mel(audio_dev, h->mel_window, h->mel_twiddle, h->mel_fb, mel_ncl_dev, B, Ls,
                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+int dc_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                    void* stream) {
+  if (rows == 0 || width_bytes == 0) return DC_OK;
+  DC_CHECK(dst && src && dst_pitch >= width_bytes && src_pitch >= width_bytes, DC_ERR_ARG, "bad argument to dc_copy2d_async");
+  DC_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDefault,
+                            reinterpret_cast<cudaStream_t>(stream)));
+  return DC_OK;
 }
 
 int dc_ncl_to_nlc(const float* in_dev, float* out_dev, int B, int C, int T, void* stream) {

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/distilcodec_b200.h"

@@ -423,12 +423,12 @@ static int launch_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
                       cudaStream_t st, int sm_count) {
   using namespace tsw;
   constexpr int TOTAL = Cfg<EG, CW, BST>::TOTAL;
-  static int attr_dev_mask = 0;
+  static std::atomic<unsigned> attr_dev_mask{0u};  // once per (function, device); atomic because host threads driving different devices meet here
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
-  if (!(attr_dev_mask & (1 << dev))) {
+  if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
     DC_CUDA(cudaFuncSetAttribute(conv_tsw_kernel<EG, CW, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
-    attr_dev_mask |= 1 << dev;
+    attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
   }
   const int tiles_per_clip = (s.T + 127) / 128;
   const long long m_tiles = (long long)s.B * tiles_per_clip;
@@ -492,12 +492,12 @@ static int launch_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvG
   using namespace ts;
   constexpr int BOX_ROWS = BOXR, TOTAL = Cfg<BOXR, AST, BST>::TOTAL;
   DC_CHECK(256 + (s.J - 1) * s.dil <= 2 * BOXR, DC_ERR_SHAPE, "conv_ts: halo does not fit the activation buffer");
-  static int attr_dev_mask = 0;
+  static std::atomic<unsigned> attr_dev_mask{0u};  // once per (function, device); atomic because host threads driving different devices meet here
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
-  if (!(attr_dev_mask & (1 << dev))) {
+  if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
     DC_CUDA(cudaFuncSetAttribute(conv_ts_kernel<BOXR, AST, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
-    attr_dev_mask |= 1 << dev;
+    attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
   }
   const int tiles_per_clip = (s.T + 255) / 256;
   const long long total = (long long)s.B * tiles_per_clip;

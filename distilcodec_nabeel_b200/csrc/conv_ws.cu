@@ -498,12 +498,12 @@ static int launch_pair(const __nv_bfloat16* S, const __nv_bfloat16* W1, const __
                        const ConvGemmShape& s1, const Epilogue& e2, cudaStream_t st, int sm_count) {
   const int J = s1.J, RA = (128 + (J - 1) * s1.dil + 7) / 8 * 8, MO = 128 - (J - 1);
   const PairLayout lay = pair_layout(C, J, RA);
-  static int attr_dev_mask = 0;
+  static std::atomic<unsigned> attr_dev_mask{0u};  // once per (function, device); atomic because host threads driving different devices meet here
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
-  if (!(attr_dev_mask & (1 << dev))) {
+  if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
     DC_CUDA(cudaFuncSetAttribute(conv_ws_pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_dev_mask |= 1 << dev;
+    attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
   }
   const int tiles_per_clip = (s1.T + MO - 1) / MO;
   const long long total = (long long)s1.B * tiles_per_clip;
@@ -562,12 +562,12 @@ static int launch_ws(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvG
                      cudaStream_t st, int sm_count) {
   const int RA = (128 + (s.J - 1) * s.dil + 7) / 8 * 8;
   const WsLayout lay = ws_layout(C, N, s.J, RA);
-  static int attr_dev_mask = 0;
+  static std::atomic<unsigned> attr_dev_mask{0u};  // once per (function, device); atomic because host threads driving different devices meet here
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
-  if (!(attr_dev_mask & (1 << dev))) {
+  if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
     DC_CUDA(cudaFuncSetAttribute(conv_ws_kernel<C, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_dev_mask |= 1 << dev;
+    attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
   }
   const int tiles_per_clip = (s.T + 127) / 128;
   const long long total = (long long)s.B * tiles_per_clip;

@@ -233,15 +233,14 @@ static int launch_cfg(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
                       cudaStream_t st, int sm_count) {
   using L = GemmTcSmem<BN, BK, STAGES, EG>;
   static_assert(ACC * BN <= 512, "TMEM columns");
-  static bool attr_set = false;  // per-process; the attribute is per-function per-device, set it for every device once
-  static int attr_dev_mask = 0;
+
+  static std::atomic<unsigned> attr_dev_mask{0u};  // once per (function, device); atomic because host threads driving different devices meet here
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
-  if (!attr_set || !(attr_dev_mask & (1 << dev))) {
+  if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
     DC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, STAGES, EG, ACC>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-    attr_dev_mask |= 1 << dev;
+    attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
   }
   const int tiles_per_clip = (s.T + 127) / 128;
   const long long m_tiles = (long long)s.B * tiles_per_clip;

@@ -384,14 +384,14 @@ static int dwconv_ln_stream_dispatch(const float* in, const float* dw_w, const f
   const unsigned grid = (unsigned)std::min<long long>(items, (long long)sms * MINB);
   const size_t smem = (size_t)NST * 8 * C * 4;
   ProfScope ps(PC_DWCONV_LN, 0, (double)B * T * C * (4.0 + (out_dt == DT_F32 ? 4.0 : 2.0)), st, "C%d", C);
-  static unsigned attr_dev_mask[2] = {0u, 0u};  // the opt-in shared-memory size is a per-device function attribute
+  static std::atomic<unsigned> attr_dev_mask[2];  // the opt-in shared-memory size is a per-device function attribute
   const int which = out_dt == DT_F32 ? 0 : 1;
-  if (!(attr_dev_mask[which] & (1u << dev))) {
+  if (!(attr_dev_mask[which].load(std::memory_order_acquire) & (1u << dev))) {
     if (which == 0)
       DC_CUDA(cudaFuncSetAttribute(dwconv_ln_stream_kernel<C, float, NST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else
       DC_CUDA(cudaFuncSetAttribute(dwconv_ln_stream_kernel<C, __nv_bfloat16, NST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_dev_mask[which] |= 1u << dev;
+    attr_dev_mask[which].fetch_or(1u << dev, std::memory_order_release);
   }
   if (which == 0)
     dwconv_ln_stream_kernel<C, float, NST, MINB><<<grid, C / 4, smem, st>>>(in, dw_w, dw_b, ln_w, ln_b, (float*)out, B, T);
@@ -578,13 +578,13 @@ int launch_conv_post_tanh(const void* in, int in_dt, const float* w_host /*[13][
   ConvPostW W;
   memcpy(W.w, w_host, sizeof(W.w));
   constexpr int SMEM = 32 * (512 + 16) * 4;
-  static int attr_dev_mask = 0;
+  static std::atomic<unsigned> attr_dev_mask{0u};  // once per (function, device); atomic because host threads driving different devices meet here
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
-  if (!(attr_dev_mask & (1 << dev))) {
+  if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
     DC_CUDA(cudaFuncSetAttribute(conv_post_tanh_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     DC_CUDA(cudaFuncSetAttribute(conv_post_tanh_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_dev_mask |= 1 << dev;
+    attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
   }
   dim3 grid((L + 511) / 512, B);
   ProfScope ps(PC_CONV_POST, 2.0 * B * (double)L * 32 * 13, (double)B * L * (32.0 * (in_dt == DT_F32 ? 4 : 2) + 4.0), st);

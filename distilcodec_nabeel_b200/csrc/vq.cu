@@ -684,12 +684,12 @@ int launch_vq_search(const void* x, int x_dt, const float* x2_opt, int64_t nrows
       const uint32_t box[2] = {VQ_BK, VQ_BN};
       DC_TRY(make_tmap_bf16(&tmC, codebook_bf16, 2, dims, strides, box, 128));
     }
-    static int attr_dev_mask = 0;
+    static std::atomic<unsigned> attr_dev_mask{0u};  // once per (function, device); atomic because host threads driving different devices meet here
     int dev = 0;
     DC_CUDA(cudaGetDevice(&dev));
-    if (!(attr_dev_mask & (1 << dev))) {
+    if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
       DC_CUDA(cudaFuncSetAttribute(vq_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VqSmem::TOTAL));
-      attr_dev_mask |= 1 << dev;
+      attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
     }
     const int grid = n_items < sm_count ? n_items : sm_count;
     vq_score_kernel<<<grid, VQ_THREADS, VqSmem::TOTAL, st>>>(tmX, tmC, c2, w.win, w.best, w.cnt, w.cand, (int)nrows,

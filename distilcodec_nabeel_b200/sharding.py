@@ -62,11 +62,37 @@ def gather_by_clip(local: torch.Tensor, n_clips: int, group=None, dst: Optional[
     return torch.cat([p[:s] for p, s in zip(parts, sizes)], 0)
 
 
+def _rows_pitch(t: torch.Tensor) -> Tuple[int, int, int]:
+    """View with a contiguous last dimension whose leading dimensions collapse into one pitch -> (rows, width_bytes,
+    pitch_bytes) for dc_copy2d_async."""
+    es = t.element_size()
+    if t.dim() == 0 or t.stride(-1) != 1 and t.shape[-1] > 1:
+        raise ValueError("copy2d: last dimension must be contiguous")
+    width = t.shape[-1]
+    rows = 1
+    pitch = width
+    lead = [(n, st) for n, st in zip(t.shape[:-1], t.stride()[:-1]) if n > 1]
+    if lead:
+        pitch = lead[-1][1]
+        expect = pitch
+        for n, st in reversed(lead):
+            if st != expect:
+                raise ValueError("copy2d: leading dimensions do not collapse into one pitch")
+            expect *= n
+            rows *= n
+    return rows, width * es, pitch * es
+
+
 class Pipeline:
     """mel (host) -> codes, waveform (host) on one GPU, in chunks of clips that fit the workspace budget.
 
     engine : distilcodec_nabeel_b200.Engine (one device, one numeric mode)
     chunk  : clips per device pass; None = as many as `engine.workspace_limit` allows for the generator stage
+
+    Every host-buffer leg is the same three-stage software pipeline over work items (a clip range x a time tile):
+    upload (copy stream) -> compute (caller's stream) -> download (copy stream), so item i+1 uploads and item i-1
+    downloads while item i computes.  Strided slices of PINNED host tensors (time tiles, per-clip crops) move by
+    dc_copy2d_async, i.e. straight by DMA without a pageable staging copy.
     """
 
     def __init__(self, engine, chunk: Optional[int] = None):
@@ -99,56 +125,106 @@ class Pipeline:
         """decode_from_codes (distil_codec.py:581-594) for a batch: codes (B,T) -> wav (B, 256T)."""
         return self.eng.generator(self.eng.decode_codes(codes_dev))
 
-    # ---- host-buffer legs ---------------------------------------------------------------------------------
-    def _run_host(self, mel_host: torch.Tensor, want_wav: bool, codes_out: torch.Tensor,
-                  wav_out: Optional[torch.Tensor]):
-        B, _, T = mel_host.shape
-        step = self._chunk(B, T)
+    def tokenize_wav_device(self, wav_padded_dev: torch.Tensor) -> torch.Tensor:
+        """audio (B, n+1) on device, already left-padded by one zero sample (distil_codec.py:134) -> codes (B,T)."""
+        return self.encode_device(self.eng.mel(wav_padded_dev))[0]
+
+    # ---- the copy / compute pipeline ----------------------------------------------------------------------
+    def _copy2d(self, dst: torch.Tensor, src: torch.Tensor, stream: torch.cuda.Stream) -> int:
+        """dst <- src (same shape; host views must be of pinned tensors) on `stream`; returns the bytes moved."""
+        if tuple(dst.shape) != tuple(src.shape) or dst.dtype != src.dtype:
+            raise ValueError(f"copy2d: {tuple(src.shape)} {src.dtype} -> {tuple(dst.shape)} {dst.dtype}")
+        if src.numel() == 0:
+            return 0
+        for t in (dst, src):
+            if not t.is_cuda and not t.is_pinned():
+                raise ValueError("copy2d: host tensors must be pinned (pageable memory would make the copy synchronous)")
+        rows, width, sp = _rows_pitch(src)
+        rows_d, width_d, dp = _rows_pitch(dst)
+        if (rows, width) != (rows_d, width_d):   # different collapses of the same shape: fall back to row = last dim
+            raise ValueError("copy2d: source and destination do not collapse to the same rows")
+        from . import _abi
+        _abi.check(self.eng.lib.dc_copy2d_async(dst.data_ptr(), dp, src.data_ptr(), sp, width, rows,
+                                                stream.cuda_stream), "dc_copy2d_async")
+        return rows * width
+
+    def _run_items(self, items: Sequence, upload, compute, download) -> None:
+        """upload(item) -> device inputs [copy stream]; compute(item, inputs) -> device outputs [current stream];
+        download(item, outputs) [copy stream, after the compute].  Item i+1 is uploaded while item i computes."""
         main = torch.cuda.current_stream(self.dev)
-        pending = None  # (event, device tensors kept alive until their D2H copy has been issued)
-        nxt = None
+        cs = self.copy_stream
+
+        def issue(item):
+            with torch.cuda.stream(cs):
+                ins = upload(item)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            return ins, ev
+
+        keep = None
         with torch.cuda.device(self.dev):
-            for b0 in range(0, B, step):
-                b1 = min(B, b0 + step)
-                if nxt is None:
-                    with torch.cuda.stream(self.copy_stream):
-                        cur = mel_host[b0:b1].to(self.dev, non_blocking=True)
-                        ev_up = torch.cuda.Event()
-                        ev_up.record(self.copy_stream)
-                else:
-                    cur, ev_up = nxt
-                self.h2d_bytes += cur.numel() * cur.element_size()
-                # prefetch the next chunk while this one computes
-                if b1 < B:
-                    b2 = min(B, b1 + step)
-                    with torch.cuda.stream(self.copy_stream):
-                        n_t = mel_host[b1:b2].to(self.dev, non_blocking=True)
-                        n_ev = torch.cuda.Event()
-                        n_ev.record(self.copy_stream)
-                    nxt = (n_t, n_ev)
-                else:
-                    nxt = None
+            cs.wait_stream(main)                       # inputs the caller produced on its stream
+            nxt = issue(items[0]) if items else None
+            for k, item in enumerate(items):
+                ins, ev_up = nxt
+                nxt = issue(items[k + 1]) if k + 1 < len(items) else None
                 main.wait_event(ev_up)
-                cur.record_stream(main)
-                if want_wav:
-                    codes, wav = self.reconstruct_device(cur)
-                else:
-                    codes, _ = self.encode_device(cur)
-                    wav = None
+                for t in ins:
+                    t.record_stream(main)
+                outs = compute(item, ins)
                 ev_done = torch.cuda.Event()
                 ev_done.record(main)
-                with torch.cuda.stream(self.copy_stream):
-                    self.copy_stream.wait_event(ev_done)
-                    codes_out[b0:b1].copy_(codes, non_blocking=True)
-                    codes.record_stream(self.copy_stream)
-                    self.d2h_bytes += codes.numel() * 8
-                    if wav is not None:
-                        wav_out[b0:b1].copy_(wav, non_blocking=True)
-                        wav.record_stream(self.copy_stream)
-                        self.d2h_bytes += wav.numel() * 4
-                pending = (codes, wav)
-        self.copy_stream.synchronize()
-        del pending
+                with torch.cuda.stream(cs):
+                    cs.wait_event(ev_done)
+                    download(item, outs)
+                    for t in outs:
+                        t.record_stream(cs)
+                keep = (ins, outs)
+            cs.synchronize()
+        del keep
+
+    def _clip_items(self, B: int, T: int):
+        step = self._chunk(B, T)
+        return [(b0, min(B, b0 + step)) for b0 in range(0, B, step)]
+
+    def _up(self, dst_dev: torch.Tensor, src_host: torch.Tensor) -> None:
+        self.h2d_bytes += self._copy2d(dst_dev, src_host, self.copy_stream)
+
+    def _down(self, dst_host: torch.Tensor, src_dev: torch.Tensor) -> None:
+        self.d2h_bytes += self._copy2d(dst_host, src_dev, self.copy_stream)
+
+    @staticmethod
+    def _pinned(t: torch.Tensor) -> torch.Tensor:
+        return t if t.is_pinned() else t.contiguous().pin_memory()
+
+    # ---- host-buffer legs ---------------------------------------------------------------------------------
+    def _run_host(self, mel_host: torch.Tensor, want_wav: bool, codes_out: torch.Tensor,
+                  wav_out: Optional[torch.Tensor], tiles=None, crop_hop: int = 0):
+        """mel_host (B,128,T) pinned.  `tiles` = [(lo, hi, s, e)] time tiles (default: the whole clip)."""
+        mel_host = self._pinned(mel_host)
+        B, M, T = mel_host.shape
+        hop = self.eng.hop
+        tiles = tiles or [(0, T, 0, T)]
+        items = [(b0, b1, *t) for t in tiles for (b0, b1) in self._clip_items(B, t[1] - t[0])]
+
+        def upload(it):
+            b0, b1, lo, hi, _, _ = it
+            cur = torch.empty(b1 - b0, M, hi - lo, dtype=torch.float32, device=self.dev)
+            self._up(cur, mel_host[b0:b1, :, lo:hi])
+            return (cur,)
+
+        def compute(it, ins):
+            if want_wav:
+                return self.reconstruct_device(ins[0])
+            return (self.encode_device(ins[0])[0],)
+
+        def download(it, outs):
+            b0, b1, lo, hi, s, e = it
+            self._down(codes_out[b0:b1, s:e], outs[0][:, s - lo:e - lo])
+            if want_wav:
+                self._down(wav_out[b0:b1, s * hop:e * hop], outs[1][:, (s - lo) * hop:(e - lo) * hop])
+
+        self._run_items(items, upload, compute, download)
 
     def reconstruct(self, mel_host: torch.Tensor, codes_out: Optional[torch.Tensor] = None,
                     wav_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -161,51 +237,119 @@ class Pipeline:
         self._run_host(mel_host, True, codes_out, wav_out)
         return codes_out, wav_out
 
-    def tokenize(self, mel_host: torch.Tensor, codes_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def tokenize(self, mel_host: torch.Tensor, codes_out: Optional[torch.Tensor] = None, tiles=None) -> torch.Tensor:
         """wav->codes leg (DistilCodec.encode, distil_codec.py:545-573) from HOST log-mel.  Returns host codes."""
         B, _, T = mel_host.shape
         if codes_out is None:
             codes_out = torch.empty(B, T, dtype=torch.int64, pin_memory=True)
-        self._run_host(mel_host, False, codes_out, None)
+        self._run_host(mel_host, False, codes_out, None, tiles)
         return codes_out
 
     def tokenize_wav(self, wav_host: torch.Tensor, codes_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """wav -> codes entirely on the device (DistilCodec.encode with raw_audio=True, distil_codec.py:545-573 +
         :99-145) from HOST audio (B, n) fp32 at the model rate, equal lengths: left-pad by one zero sample (:134), GPU
         log-mel (the reference runs this stage on the CPU), encoder, VQ.  Needs the engine's mel buffers."""
+        wav_host = self._pinned(wav_host)
         B, n = wav_host.shape
         T = (n + 1 - 256) // 256 + 1
         if codes_out is None:
             codes_out = torch.empty(B, T, dtype=torch.int64, pin_memory=True)
-        step = self._chunk(B, T)
-        with torch.cuda.device(self.dev):
-            for b0 in range(0, B, step):
-                b1 = min(B, b0 + step)
-                w = wav_host[b0:b1].to(self.dev, non_blocking=True)
-                self.h2d_bytes += w.numel() * 4
-                mel = self.eng.mel(torch.nn.functional.pad(w, (1, 0)).contiguous())
-                codes, _ = self.encode_device(mel)
-                codes_out[b0:b1].copy_(codes, non_blocking=True)
-                self.d2h_bytes += codes.numel() * 8
-            torch.cuda.current_stream(self.dev).synchronize()
+
+        def upload(it):
+            b0, b1 = it
+            w = torch.empty(b1 - b0, n + 1, dtype=torch.float32, device=self.dev)
+            w[:, :1].zero_()                             # the reference's one-sample left pad (distil_codec.py:134)
+            self._up(w[:, 1:], wav_host[b0:b1])
+            return (w,)
+
+        def compute(it, ins):
+            return (self.tokenize_wav_device(ins[0]),)
+
+        def download(it, outs):
+            self._down(codes_out[it[0]:it[1]], outs[0])
+
+        self._run_items(self._clip_items(B, T), upload, compute, download)
         return codes_out
 
-    def decode(self, codes_host: torch.Tensor, wav_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def tokenize_wav_ragged(self, wavs: Sequence, lengths_out: Optional[list] = None) -> List[torch.Tensor]:
+        """Clips of different lengths exactly as `preprocess_raw_audio_batch` + `encode` treat them
+        (distil_codec.py:99-145, 556-563): every clip is right-padded with zero AUDIO to the longest of the call, the
+        whole batch is tokenised, and clip i keeps its first `n_i // 256` codes.  -> list of host int64 code tensors."""
+        ns = [int(w.shape[-1]) for w in wavs]
+        if not ns:
+            return []
+        mx = max(ns)
+        batch = torch.zeros(len(ns), mx, dtype=torch.float32).pin_memory()
+        for i, w in enumerate(wavs):
+            batch[i, :ns[i]] = torch.as_tensor(w, dtype=torch.float32).reshape(-1)
+        codes = self.tokenize_wav(batch)
+        if lengths_out is not None:
+            lengths_out.extend(n // self.eng.hop for n in ns)
+        return [codes[i, :ns[i] // self.eng.hop].clone() for i in range(len(ns))]
+
+    def decode(self, codes_host: torch.Tensor, wav_out: Optional[torch.Tensor] = None, tiles=None) -> torch.Tensor:
         """codes->wav leg (decode_from_codes, distil_codec.py:581-594) from HOST codes (B,T) int64."""
+        codes_host = self._pinned(codes_host)
         B, T = codes_host.shape
+        hop = self.eng.hop
         if wav_out is None:
-            wav_out = torch.empty(B, T * self.eng.hop, dtype=torch.float32, pin_memory=True)
-        step = self._chunk(B, T)
-        with torch.cuda.device(self.dev):
-            for b0 in range(0, B, step):
-                b1 = min(B, b0 + step)
-                c = codes_host[b0:b1].to(self.dev, non_blocking=True)
-                self.h2d_bytes += c.numel() * 8
-                wav = self.decode_device(c)
-                wav_out[b0:b1].copy_(wav, non_blocking=True)
-                self.d2h_bytes += wav.numel() * 4
-            torch.cuda.current_stream(self.dev).synchronize()
+            wav_out = torch.empty(B, T * hop, dtype=torch.float32, pin_memory=True)
+        tiles = tiles or [(0, T, 0, T)]
+        items = [(b0, b1, *t) for t in tiles for (b0, b1) in self._clip_items(B, t[1] - t[0])]
+
+        def upload(it):
+            b0, b1, lo, hi, _, _ = it
+            c = torch.empty(b1 - b0, hi - lo, dtype=torch.int64, device=self.dev)
+            self._up(c, codes_host[b0:b1, lo:hi])
+            return (c,)
+
+        def compute(it, ins):
+            return (self.decode_device(ins[0]),)
+
+        def download(it, outs):
+            b0, b1, lo, hi, s, e = it
+            self._down(wav_out[b0:b1, s * hop:e * hop], outs[0][:, (s - lo) * hop:(e - lo) * hop])
+
+        self._run_items(items, upload, compute, download)
         return wav_out
+
+    def decode_ragged(self, codes_list: Sequence, tails: str = "exact") -> List[torch.Tensor]:
+        """Batched decode of code sequences of different lengths — what `decode_from_codes_batch` is meant to do
+        (distil_codec.py:598-639: right-pad with code 0 to the longest, decode the batch, split per clip; the
+        reference's own layout bug makes it decode clip 0 only) plus `save_wav`'s per-clip crop (:640-654).
+        -> list of host fp32 waveforms, clip i of length `256 * len(codes_i)`.
+
+        tails="padded": clip i is the batch row cropped, i.e. identical to `decode_from_codes` of the RIGHT-PADDED
+                        sequence (its last ~25 frames see the code-0 padding as right context).
+        tails="exact" : identical to `decode_from_codes(codes_i)` of the clip alone (length mask): the last
+                        DECODE_HALO frames of every shorter clip are re-decoded from a tile that ends at the clip's own
+                        end, where the convolutions see their zero padding (bit-exact, same argument as time tiling)."""
+        if tails not in ("exact", "padded"):
+            raise ValueError("tails must be 'exact' or 'padded'")
+        lens = [int(len(c)) for c in codes_list]
+        if not lens:
+            return []
+        hop = self.eng.hop
+        mx = max(lens)
+        batch = torch.zeros(len(lens), max(mx, 1), dtype=torch.int64).pin_memory()
+        for i, c in enumerate(codes_list):
+            batch[i, :lens[i]] = torch.as_tensor(c, dtype=torch.int64).reshape(-1)
+        wav = self.decode(batch)
+        outs = [wav[i, :lens[i] * hop].clone() for i in range(len(lens))]
+        if tails == "exact":
+            H = DECODE_HALO
+            short = [i for i, n in enumerate(lens) if 0 < n < mx]
+            # tail tiles of 2H frames ending at the clip end (whole clip when it is shorter than that), grouped by size
+            by_len = {}
+            for i in short:
+                by_len.setdefault(min(lens[i], 2 * H), []).append(i)
+            for L, idx in by_len.items():
+                tail_codes = torch.stack([batch[i, lens[i] - L:lens[i]] for i in idx]).pin_memory()
+                tw = self.decode(tail_codes)
+                keep = min(L, H)
+                for r, i in enumerate(idx):
+                    outs[i][(lens[i] - keep) * hop:] = tw[r, (L - keep) * hop:]
+        return outs
 
 
 # ---- time tiling (SURVEY.md section 8 row f-3): clips longer than one workspace -------------------------------------
@@ -233,28 +377,43 @@ def time_tiles(T: int, tile: int, halo: int):
 def tokenize_long(pipe: "Pipeline", mel_host: torch.Tensor, tile: int = 8192,
                   codes_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """wav->codes leg for clips of any length with device memory bounded by `tile` frames: HOST log-mel (B,128,T) ->
-    host codes (B,T), identical to `Pipeline.tokenize` on the whole clip."""
-    B, _, T = mel_host.shape
-    if codes_out is None:
-        codes_out = torch.empty(B, T, dtype=torch.int64, pin_memory=True)
-    for lo, hi, s, e in time_tiles(T, tile, ENCODE_HALO):
-        c = pipe.tokenize(mel_host[:, :, lo:hi].contiguous())
-        codes_out[:, s:e] = c[:, s - lo:e - lo]
-    return codes_out
+    host codes (B,T), identical to `Pipeline.tokenize` on the whole clip.  Tiles move between the pinned host tensors
+    and the device by strided DMA and are double-buffered like every host-buffer leg."""
+    T = mel_host.shape[2]
+    return pipe.tokenize(mel_host, codes_out, tiles=time_tiles(T, tile, ENCODE_HALO))
 
 
 def decode_long(pipe: "Pipeline", codes_host: torch.Tensor, tile: int = 8192,
                 wav_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """codes->wav leg for clips of any length: HOST codes (B,T) -> host waveform (B, hop*T), identical to
     `Pipeline.decode` on the whole clip."""
-    B, T = codes_host.shape
+    T = codes_host.shape[1]
+    return pipe.decode(codes_host, wav_out, tiles=time_tiles(T, tile, DECODE_HALO))
+
+
+def tokenize_long_device(pipe: "Pipeline", mel_dev: torch.Tensor, tile: int = 8192) -> torch.Tensor:
+    """`tokenize_long` with the log-mel already in HBM: -> device codes (B,T)."""
+    B, _, T = mel_dev.shape
+    codes = torch.empty(B, T, dtype=torch.int64, device=mel_dev.device)
+    step = pipe._chunk(B, min(T, tile + 2 * ENCODE_HALO))
+    for lo, hi, s, e in time_tiles(T, tile, ENCODE_HALO):
+        for b0 in range(0, B, step):
+            c, _ = pipe.encode_device(mel_dev[b0:b0 + step, :, lo:hi].contiguous())
+            codes[b0:b0 + step, s:e] = c[:, s - lo:e - lo]
+    return codes
+
+
+def decode_long_device(pipe: "Pipeline", codes_dev: torch.Tensor, tile: int = 8192) -> torch.Tensor:
+    """`decode_long` with the codes already in HBM: -> device waveform (B, hop*T)."""
+    B, T = codes_dev.shape
     hop = pipe.eng.hop
-    if wav_out is None:
-        wav_out = torch.empty(B, T * hop, dtype=torch.float32, pin_memory=True)
+    wav = torch.empty(B, T * hop, dtype=torch.float32, device=codes_dev.device)
+    step = pipe._chunk(B, min(T, tile + 2 * DECODE_HALO))
     for lo, hi, s, e in time_tiles(T, tile, DECODE_HALO):
-        w = pipe.decode(codes_host[:, lo:hi].contiguous())
-        wav_out[:, s * hop:e * hop] = w[:, (s - lo) * hop:(e - lo) * hop]
-    return wav_out
+        for b0 in range(0, B, step):
+            w = pipe.decode_device(codes_dev[b0:b0 + step, lo:hi].contiguous())
+            wav[b0:b0 + step, s * hop:e * hop] = w[:, (s - lo) * hop:(e - lo) * hop]
+    return wav
 
 
 def run_sharded(fn, items: Sequence, world_size: int, rank: int):

@@ -139,6 +139,14 @@ int dc_generator_forward(dc_handle h, const float* z_nlc_dev, int B, int T, floa
  *   mel_ncl_dev : fp32 (B, 128, T), T = (Ls - 256) / 256 + 1 (integer division) */
 int dc_mel_forward(dc_handle h, const float* audio_dev, int B, int Ls, float* mel_ncl_dev, void* stream);
 
+/* Strided host<->device (or device<->device) copy of `rows` rows of `width_bytes`, enqueued on `stream` — the time
+ * tiles and per-clip crops of the host-buffer legs (mel[:, :, lo:hi] in, codes[:, s:e] / wav[:, s*256:e*256] out:
+ * the slicing `save_wav` does, distil_codec.py:640-654, and the `[:hop_len]` crops of `encode`, :556-570) move
+ * straight between PINNED host tensors and the device by DMA, with no pageable staging copy.  Pointers may be host
+ * (pinned, for the copy to be asynchronous) or device; the current device must be the one that owns the device side. */
+int dc_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                    void* stream);
+
 /* Layout helpers between the reference's channels-first tensors and the ABI's channels-last ones. */
 int dc_ncl_to_nlc(const float* in_dev, float* out_dev, int B, int C, int T, void* stream);
 int dc_nlc_to_ncl(const float* in_dev, float* out_dev, int B, int T, int C, void* stream);

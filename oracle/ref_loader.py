@@ -1,6 +1,10 @@
-"""Import the REAL reference (`/root/reference/distilcodec`) on CPU behind five stub modules.
-TEST INFRASTRUCTURE (oracle/): used only by tests/ and tests/golden/make_golden.py, and only in the dev
-container — `/root/reference` does not exist on the GPU box, where `available()` is False.
+"""Import the REAL reference (`distilcodec` package) behind five stub modules.
+TEST INFRASTRUCTURE (oracle/): used only by tests/, tests/golden/make_golden.py and bench.py's CPU legs.
+
+Where the reference is looked for, in order: `$DISTILCODEC_REFERENCE`, `/root/reference` (dev container only — it
+does not exist on the GPU box), `baseline/_ref/` (the reference `pip install --target`-ed by `__graft_entry__.build()`;
+git-ignored, but it travels to the GPU box with the repo snapshot, so the reference-backed tests and the
+`--impl reference` arm run the reference's own modules there too).
 
 Stub recipe: SURVEY.md Appendix B (soundfile, librosa, matplotlib, vector_quantize_pytorch, einx.get_at).
 """
@@ -14,17 +18,28 @@ import warnings
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-REFERENCE_ROOT = os.environ.get("DISTILCODEC_REFERENCE", "/root/reference")
+_REPO = os.path.dirname(_HERE)
+_CANDIDATES = [os.environ.get("DISTILCODEC_REFERENCE"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+
+
+def _find_root():
+    for c in _CANDIDATES:
+        if c and os.path.isfile(os.path.join(c, "distilcodec", "distil_codec.py")):
+            return c
+    return None
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "distilcodec", "distil_codec.py"))
+    return REFERENCE_ROOT is not None
 
 
 def import_reference():
     """-> the reference's `distilcodec` package (imported once)."""
     if not available():
-        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+        raise RuntimeError(f"reference not found (looked in {[c for c in _CANDIDATES if c]})")
     shims = os.path.join(_HERE, "shims")
     for p in (REFERENCE_ROOT, shims):
         if p not in sys.path:

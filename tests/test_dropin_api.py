@@ -1,12 +1,10 @@
-"""The drop-in boundary against the REAL reference API (dev container only: needs /root/reference).
+"""The drop-in boundary against the REAL reference API (needs the reference: /root/reference or baseline/_ref).
 
 `patch(codec)` replaces the three attributes of a real `DistilCodec` (distil_codec.py:52-54); its public methods then
 run unchanged on the shim modules.  There is no GPU here, so the shims' engine is replaced by an oracle-backed stand-in
 (test infrastructure; the product has no CPU path) — what is under test is the CONTRACT between the unchanged reference
 methods and the shim modules: argument layouts, GRVQResult fields, per-clip post-processing, token bookkeeping."""
 import copy
-import wave
-import os
 
 import numpy as np
 import pytest
@@ -16,7 +14,7 @@ from oracle import ref_loader
 from oracle import restatement as R
 from tests.conftest import state_dict
 
-pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference not importable (neither /root/reference nor baseline/_ref)")
 
 
 class OracleEngine:
@@ -54,8 +52,10 @@ def codecs():
 
 
 def _pcm(seconds=1.0):
-    w = wave.open(os.path.join(ref_loader.REFERENCE_ROOT, "data", "org_audios", "0001.wav"))
-    return np.frombuffer(w.readframes(int(seconds * 24000)), dtype=np.int16).astype(np.float32) / 32768.0
+    """the first seconds of the reference's data/org_audios/0001.wav (committed in tests/golden/audio_W0.npz, so the
+    test also runs where only the installed package baseline/_ref is present)"""
+    from tests.conftest import golden
+    return golden("audio_W0.npz")["pcm"][:int(seconds * 24000)].copy()
 
 
 def test_patch_replaces_exactly_the_three_attributes(codecs):

@@ -9,7 +9,7 @@ from oracle import restatement as R
 from tests.conftest import rel_err, state_dict
 from tests.golden.inputs import make_mel
 
-pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference not importable (neither /root/reference nor baseline/_ref)")
 
 
 @pytest.fixture(scope="module")
