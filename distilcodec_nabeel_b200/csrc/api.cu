@@ -116,6 +116,10 @@ struct Dense {  // one shifted-row implicit GEMM layer
   __nv_bfloat16* w_bf16 = nullptr;  // [N][J*C]   (DC_MODE_BF16)
   float* w_f32 = nullptr;           // [J*C][N]   (DC_MODE_FP32)
   const float* bias = nullptr;      // [N]
+  // block-Toeplitz "phase form" for the C = 32 ResBlock convs with dilation 1 (conv_pair.cu): one accumulator row =
+  // two time steps, W[(r, co)][(o, ci)] = w[co, ci, tap o - r] (zero outside 0..J-1), and the bias repeated twice
+  __nv_bfloat16* w_phase = nullptr; // [2N][(J+1)*C]
+  float* bias2x = nullptr;          // [2N]
 };
 
 struct Block {  // ConvNeXtBlock, models/convnext_utils.py:217-282
@@ -151,6 +155,7 @@ struct dc_handle_s {
   bool vq_tc = true;
   bool vq_x2_exact = false;
   bool fuse_pairs = true;
+  bool pairx = true;  // C = 32 stage: fp32-stream fused pair kernel (conv_pair.cu) instead of conv_ws_pair
   int epi_prefetch = 1;
 
   // encoder
@@ -322,7 +327,24 @@ static int pack_wn_conv(dc_handle_s* h, const std::string& p, bool transposed, i
   const int d0 = (int)v->shape[0], d1 = (int)v->shape[1], k = (int)v->shape[2];
   DC_TRY(launch_weight_norm_fold(g->d, v->d, scratch, d0, d1 * k, st));
   if (transposed) return pack_dense(h, scratch, true, d1, d0, k, stride, pad, 1, b->d, d, st);
-  return pack_dense(h, scratch, false, d0, d1, k, 1, pad, dil, b->d, d, st);
+  DC_TRY(pack_dense(h, scratch, false, d0, d1, k, 1, pad, dil, b->d, d, st));
+  if (h->mode == DC_MODE_BF16 && d0 == 32 && d1 == 32 && dil == 1 && (k & 1) && k >= 3 && k <= 11) {
+    // phase form of the narrowest stage's dilation-1 convs (conv_pair.cu)
+    PackDesc pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.N = 2 * d0; pd.J = k + 1; pd.C = d1; pd.phases = 2;
+    pd.s_n = (long long)d1 * k; pd.s_c = k; pd.s_k = 1;
+    for (int r = 0; r < 2; ++r)
+      for (int o = 0; o <= k; ++o) pd.kmap[r * (k + 1) + o] = (o - r >= 0 && o - r < k) ? o - r : -1;
+    DC_TRY(dev_alloc(h, &d->w_phase, (size_t)pd.N * pd.J * pd.C));
+    DC_TRY(launch_pack_weight(scratch, pd, nullptr, d->w_phase, st));
+    DC_TRY(dev_alloc(h, &d->bias2x, (size_t)2 * d0));
+    ProfScope ps(PC_PREPACK, 0, 0, st);
+    tile_bias_kernel<<<1, 256, 0, st>>>(b->d, d->bias2x, d0, 2);
+    ++g_launches_api;
+    DC_CUDA(cudaGetLastError());
+  }
+  return DC_OK;
 }
 
 static int pack_block(dc_handle_s* h, const std::string& p, Block* blk, cudaStream_t st) {
@@ -542,6 +564,20 @@ static int stage_decode_codes(const dc_handle_s* h, const int64_t* codes, int B,
   return quantizer_tail(h, fup_op, B, T, x, a, hid, qd, z_out, st);
 }
 
+// every ResBlock step of decoder stage i can run on the fp32-stream fused pair kernel (conv_pair.cu)
+static bool stage_uses_pairx(const dc_handle_s* h, int i, int B, int L) {
+  if (h->mode != DC_MODE_BF16 || !h->fuse_pairs || !h->pairx) return false;
+  for (int b = 0; b < 3; ++b)
+    for (int n3 = 0; n3 < 3; ++n3) {
+      const Dense &c1 = h->rb[i][b][0][n3], &c2 = h->rb[i][b][1][n3];
+      ConvGemmShape s1{B, L, c1.C, c1.J, c1.shift0, c1.dil, c1.N, c1.alg_scale, c1.phase_cols, c1.zero_taps};
+      ConvGemmShape s2{B, L, c2.C, c2.J, c2.shift0, c2.dil, c2.N, c2.alg_scale, c2.phase_cols, c2.zero_taps};
+      if (!conv_pairx_supported(s1, s2) || !c1.bias || !c2.w_phase || !c2.bias2x) return false;
+      if (c1.dil == 1 && !c1.w_phase) return false;
+    }
+  return true;
+}
+
 static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, float* wav, Arena& ar, bool dry,
                            cudaStream_t st) {
   const dc_config& c = h->cfg;
@@ -581,6 +617,53 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
     L = Lin * c.up_rates[i];
     const size_t n = (size_t)B * L * Cout;
     ar.release(m0);
+    if (stage_uses_pairx(h, i, B, L)) {
+      // Narrowest stage (C = 32): the activation stream is ONE fp32 tensor per step; each fused ResBlock step reads
+      // x (with its halo) and writes x' (conv_pair.cu), ping-ponging T0 / T1 because a launch must not write the
+      // tensor whose halo rows other CTAs are still reading.
+      float* x = reinterpret_cast<float*>(ar.get(n * 4));
+      float* Xb[2] = {reinterpret_cast<float*>(ar.get(n * 4)), reinterpret_cast<float*>(ar.get(n * 4))};
+      float* Tp[2] = {reinterpret_cast<float*>(ar.get(n * 4)), reinterpret_cast<float*>(ar.get(n * 4))};
+      if (!dry) {
+        {  // silu -> ConvTranspose1d (generators.py:125-126): only the fp32 result is stored
+          Epilogue e;
+          e.out0 = x;
+          e.out0_dt = DT_F32;
+          DC_TRY(run_dense(h, h->ups[i], carry[cur], B, Lin, e, st));
+        }
+        for (int b = 0; b < 3; ++b) {
+          const float* in = x;
+          for (int n3 = 0; n3 < 3; ++n3) {
+            const Dense &c1 = h->rb[i][b][0][n3], &c2 = h->rb[i][b][1][n3];
+            Epilogue e2;  // x' = c2(silu(c1(silu(x)))) + x
+            e2.res = in;
+            e2.res_dt = DT_F32;
+            float* out = nullptr;
+            if (n3 < 2 || b < 2) {
+              out = n3 < 2 ? Tp[n3] : Xb[b];
+              e2.out0 = out;
+              e2.out0_dt = DT_F32;
+            } else {  // last conv of the last branch: fold the 3-branch mean and the next op's silu
+              e2.add1 = Xb[0];
+              e2.add2 = Xb[1];
+              e2.add_dt = DT_F32;
+              e2.scale = 1.f / 3.f;
+              e2.out1 = carry[cur ^ 1];
+              e2.out1_dt = ad;
+            }
+            e2.prefetch = h->epi_prefetch;
+            ConvGemmShape s1{B, L, c1.C, c1.J, c1.shift0, c1.dil, c1.N, c1.alg_scale, c1.phase_cols, c1.zero_taps};
+            ConvGemmShape s2{B, L, c2.C, c2.J, c2.shift0, c2.dil, c2.N, c2.alg_scale, c2.phase_cols, c2.zero_taps};
+            DC_TRY(launch_conv_pairx(in, c1.dil == 1 ? c1.w_phase : c1.w_bf16, c2.w_phase, c1.bias, c2.bias2x, s1, s2, e2,
+                                     st, h->sm_count));
+            in = out;
+          }
+        }
+      }
+      cur ^= 1;
+      C = Cout;
+      continue;
+    }
     float* x = reinterpret_cast<float*>(ar.get(n * 4));
     void* sx = ar.get(n * es);
     float* X[3] = {reinterpret_cast<float*>(ar.get(n * 4)), reinterpret_cast<float*>(ar.get(n * 4)),
@@ -606,8 +689,11 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
           e2.res_dt = DT_F32;
           // bf16 silu(x') for the next step: the fused kernel must not write the buffer it is reading (halo rows
           // of neighbouring tiles), so it ping-pongs between sb and tb (tb is free there: t never leaves the chip)
+          // Unfused steps need an intermediate t buffer distinct from both their input and their bf16 output (conv2
+          // reads it with a halo while writing); their output may overwrite their input (conv1 is done with it).
           const bool fused = pair_fuses(h, h->rb[i][b][0][n3], h->rb[i][b][1][n3], B, L);
-          void* s_out = (fused && cur_s == sb) ? tb : sb;
+          void* inter = (cur_s == tb) ? sb : tb;
+          void* s_out = fused ? ((cur_s == sb) ? tb : sb) : ((inter == sb) ? tb : sb);
           if (n3 < 2) {
             e2.out0 = X[b];
             e2.out0_dt = DT_F32;
@@ -624,7 +710,7 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
             e2.out1 = carry[cur ^ 1];
             e2.out1_dt = ad;
           }
-          DC_TRY(run_conv_pair(h, h->rb[i][b][0][n3], h->rb[i][b][1][n3], cur_s, tb, B, L, e2, st));
+          DC_TRY(run_conv_pair(h, h->rb[i][b][0][n3], h->rb[i][b][1][n3], cur_s, inter, B, L, e2, st));
           cur_x = X[b];
           cur_s = s_out;
         }
@@ -750,6 +836,8 @@ int dc_set_option(dc_handle h, const char* key, double value) {
     h->vq_x2_exact = value != 0.0;
   } else if (!strcmp(key, "fuse_pairs")) {
     h->fuse_pairs = value != 0.0;
+  } else if (!strcmp(key, "pairx")) {
+    h->pairx = value != 0.0;
   } else if (!strcmp(key, "epi_prefetch")) {
     h->epi_prefetch = (int)value;
   } else {
@@ -1246,7 +1334,8 @@ int dc_profile_collect(dc_profile_row* rows, int cap, int* n) {
 
 uint64_t dc_launch_count(void) {
   return g_launches_api + gemm_tc_launch_count() + gemm_f32_launch_count() + pointwise_launch_count() +
-         vq_launch_count() + conv_ws_launch_count() + mel_launch_count() + conv_ts_launch_count();
+         vq_launch_count() + conv_ws_launch_count() + mel_launch_count() + conv_ts_launch_count() +
+         conv_pairx_launch_count();
 }
 
 }  // extern "C"

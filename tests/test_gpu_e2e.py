@@ -283,3 +283,30 @@ def test_two_devices_in_one_process_agree():
         outs.append((c.cpu(), w.cpu()))
         eng.close()
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("variant", ["W0", "W1"])
+def test_fp32_stream_pair_kernel_matches_oracle_and_the_two_kernel_form(variant):
+    """Narrowest decoder stage (C = 32): the fused ResBlock-step kernel with the fp32 activation stream and
+    block-Toeplitz weights (conv_pair.cu) against (a) the oracle and (b) the same engine with the kernel switched off
+    (conv_ws_pair / two-kernel form: same bf16 operands, different fp32 summation order)."""
+    sd = state_dict(variant)
+    eng = engine(variant, "bf16")
+    for B, T, seed in ((3, 37, 31), (2, 301, 32), (1, 1, 33)):
+        z = make_latents(B, T, seed=seed) * 0.5
+        ref = R.generator_forward(sd, z)[:, 0]
+        zd = z.transpose(1, 2).contiguous().to(eng.device)
+        try:
+            eng.set_option("pairx", 1)
+            n0 = eng.launch_count()
+            wav_new = eng.generator(zd)
+            n_new = eng.launch_count() - n0
+            eng.set_option("pairx", 0)
+            n0 = eng.launch_count()
+            wav_old = eng.generator(zd)
+            n_old = eng.launch_count() - n0
+        finally:
+            eng.set_option("pairx", 1)
+        assert n_new == n_old                                   # one launch per ResBlock step either way
+        assert rel_err(wav_new, ref) < TOL["bf16"], (B, T)
+        assert rel_err(wav_new, wav_old) < 2e-4, (B, T)          # only the summation order differs
