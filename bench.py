@@ -56,7 +56,7 @@ WORKLOADS = {
     "bulk_10min": "BASELINE configs[4]: tokenise + codes->wav decode of {clips} synthetic {secs:g} s clips per GPU "
                   "through the time-tiled legs",
 }
-DEFAULT_SHAPE = {"recon": (256, 10.0), "vq_only": (64, 10.0), "wav2codes_30s": (64, 30.0), "bulk_10min": (2, 600.0)}
+DEFAULT_SHAPE = {"recon": (256, 10.0), "vq_only": (64, 10.0), "wav2codes_30s": (64, 30.0), "bulk_10min": (4, 600.0)}
 
 
 def load_peaks():
@@ -262,12 +262,7 @@ class VqOnly(Workload):
         self.codes = self.eng.vq_search(self.x_dev[i & 1])
 
     def host_step(self, i):
-        x = self.x_host[i & 1].to(self.dev, non_blocking=True)
-        self.pipe.h2d_bytes += x.numel() * 2
-        c = self.eng.vq_search(x)
-        self.codes_host.copy_(c, non_blocking=True)
-        self.pipe.d2h_bytes += c.numel() * 8
-        torch.cuda.current_stream(self.dev).synchronize()
+        self.pipe.vq_search(self.x_host[i & 1], self.codes_host)
 
 
 class Wav2Codes(Workload):
@@ -375,7 +370,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine tunable key=value (dc_set_option), repeatable")
     ap.add_argument("--chunk", type=int, default=0, help="clips per device pass of the host-buffer leg; 0 = default")
-    ap.add_argument("--tile", type=int, default=8192, help="frames per time tile (bulk_10min)")
+    ap.add_argument("--tile", type=int, default=16384, help="frames per time tile (bulk_10min)")
     ap.add_argument("--cpu-clips", type=int, default=0, help="bounded CPU sample: clips per step (default 1; 2 in "
                                                              "the GPU arm's cpu_baseline)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

@@ -11,8 +11,8 @@ from .modules import (B200Encoder, B200Generator, B200MelSpectrogram, B200Quanti
                       build_modules, mel_buffers, patch)
 from .sharding import (Pipeline, decode_long, decode_long_device, gather_by_clip, shard_clips, time_tiles, tokenize_long,
                        tokenize_long_device)
-from . import bulk
+from . import audio, bulk
 
 __all__ = ["Engine", "EngineSet", "B200Encoder", "B200Quantizer", "B200Generator", "GRVQResult", "Pipeline",
            "build_modules", "patch", "B200MelSpectrogram", "mel_buffers", "load_config", "shard_clips", "gather_by_clip", "tokenize_long", "decode_long",
-           "tokenize_long_device", "decode_long_device", "time_tiles", "_abi"]
+           "tokenize_long_device", "decode_long_device", "time_tiles", "audio", "bulk", "_abi"]

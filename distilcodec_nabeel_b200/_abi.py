@@ -25,6 +25,12 @@ class DcConfig(C.Structure):
                 ("post_kernel", C.c_int)]
 
 
+class DcAudioInfo(C.Structure):
+    """dc_audio_info"""
+    _fields_ = [("sample_rate", C.c_int), ("channels", C.c_int), ("bits_per_sample", C.c_int), ("is_float", C.c_int),
+                ("frames", C.c_int64)]
+
+
 class DcProfileRow(C.Structure):
     """dc_profile_row: per-kernel-class device time and algorithmic work."""
     _fields_ = [("name", C.c_char * 64), ("launches", C.c_uint64), ("ms", C.c_double), ("flops", C.c_double),
@@ -52,6 +58,13 @@ SIGNATURES = {
     "dc_generator_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "dc_mel_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "dc_copy2d_async": (_i, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
+    "dc_audio_probe": (_i, [C.c_char_p, C.POINTER(DcAudioInfo)]),
+    "dc_audio_resampled_length": (_i, [_i64, _i, _i, C.POINTER(_i64)]),
+    "dc_audio_resample": (_i, [_vp, _i64, _i, _i, _i, C.c_double, _vp, _i64, C.POINTER(_i64), _i]),
+    "dc_audio_load": (_i, [C.c_char_p, _i, _i, C.c_double, _i64, _i64, _vp, _i64, C.POINTER(_i64), C.POINTER(_i)]),
+    "dc_audio_load_batch": (_i, [C.POINTER(C.c_char_p), _i, _i, _i, C.c_double, _vp, _i64, _i64, _vp,
+                                 C.POINTER(_i), _i]),
+    "dc_audio_write_wav": (_i, [C.c_char_p, _vp, _i64, _i]),
     "dc_ncl_to_nlc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "dc_nlc_to_ncl": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "dc_op_conv_gemm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdistilcodec_b200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "conv_ws.cu", "conv_pair.cu", "conv_ts.cu", "gemm_f32.cu", "pointwise.cu", "vq.cu", "mel.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "conv_ws.cu", "conv_pair.cu", "conv_ts.cu", "gemm_f32.cu", "pointwise.cu", "vq.cu", "mel.cu", "audio_io.cpp"]
 HEADERS = ["common.cuh", "ptx.cuh", "epilogue.cuh", os.path.join("..", "..", "include", "distilcodec_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -45,7 +45,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), lib: str =
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []

@@ -155,7 +155,9 @@ struct dc_handle_s {
   bool vq_tc = true;
   bool vq_x2_exact = false;
   bool fuse_pairs = true;
-  bool pairx = true;  // C = 32 stage: fp32-stream fused pair kernel (conv_pair.cu) instead of conv_ws_pair
+  // C = 32 stage, fused ResBlock steps: 0 = conv_ws_pair (conv_ws.cu); 1 = conv_pair.cu on the fp32 stream (no bf16 side
+  // buffer); 2 = conv_pair.cu with the bf16 side buffer as input (phase-form MMAs, data flow of conv_ws_pair)
+  int pairx = 2;
   int epi_prefetch = 1;
 
   // encoder
@@ -401,6 +403,11 @@ static int run_conv_pair(const dc_handle_s* h, const Dense& c1, const Dense& c2,
   ConvGemmShape s2{B, T, c2.C, c2.J, c2.shift0, c2.dil, c2.N, c2.alg_scale, c2.phase_cols, c2.zero_taps};
   if (pair_fuses(h, c1, c2, B, T)) {
     DC_CHECK(e2.out1 != S && e2.out0 != S, DC_ERR_ARG, "fused conv pair: an output aliases the activation input");
+    if (h->pairx == 2 && conv_pairx_supported(s1, s2) && c2.w_phase && c2.bias2x && (c1.dil != 1 || c1.w_phase)) {
+      e2.prefetch = h->epi_prefetch;
+      return launch_conv_pairx(nullptr, reinterpret_cast<const __nv_bfloat16*>(S), c1.dil == 1 ? c1.w_phase : c1.w_bf16,
+                               c2.w_phase, c1.bias, c2.bias2x, s1, s2, e2, st, h->sm_count);
+    }
     if (!e2.bias) e2.bias = c2.bias;
     e2.ldo = c2.N;
     e2.prefetch = h->epi_prefetch;
@@ -566,7 +573,7 @@ static int stage_decode_codes(const dc_handle_s* h, const int64_t* codes, int B,
 
 // every ResBlock step of decoder stage i can run on the fp32-stream fused pair kernel (conv_pair.cu)
 static bool stage_uses_pairx(const dc_handle_s* h, int i, int B, int L) {
-  if (h->mode != DC_MODE_BF16 || !h->fuse_pairs || !h->pairx) return false;
+  if (h->mode != DC_MODE_BF16 || !h->fuse_pairs || h->pairx != 1) return false;
   for (int b = 0; b < 3; ++b)
     for (int n3 = 0; n3 < 3; ++n3) {
       const Dense &c1 = h->rb[i][b][0][n3], &c2 = h->rb[i][b][1][n3];
@@ -654,8 +661,8 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
             e2.prefetch = h->epi_prefetch;
             ConvGemmShape s1{B, L, c1.C, c1.J, c1.shift0, c1.dil, c1.N, c1.alg_scale, c1.phase_cols, c1.zero_taps};
             ConvGemmShape s2{B, L, c2.C, c2.J, c2.shift0, c2.dil, c2.N, c2.alg_scale, c2.phase_cols, c2.zero_taps};
-            DC_TRY(launch_conv_pairx(in, c1.dil == 1 ? c1.w_phase : c1.w_bf16, c2.w_phase, c1.bias, c2.bias2x, s1, s2, e2,
-                                     st, h->sm_count));
+            DC_TRY(launch_conv_pairx(in, nullptr, c1.dil == 1 ? c1.w_phase : c1.w_bf16, c2.w_phase, c1.bias, c2.bias2x, s1,
+                                     s2, e2, st, h->sm_count));
             in = out;
           }
         }
@@ -837,7 +844,8 @@ int dc_set_option(dc_handle h, const char* key, double value) {
   } else if (!strcmp(key, "fuse_pairs")) {
     h->fuse_pairs = value != 0.0;
   } else if (!strcmp(key, "pairx")) {
-    h->pairx = value != 0.0;
+    DC_CHECK(value == 0.0 || value == 1.0 || value == 2.0, DC_ERR_ARG, "pairx must be 0, 1 or 2");
+    h->pairx = (int)value;
   } else if (!strcmp(key, "epi_prefetch")) {
     h->epi_prefetch = (int)value;
   } else {

@@ -145,11 +145,12 @@ int launch_conv_ws_pair(const __nv_bfloat16* S, const __nv_bfloat16* W1, const _
                         const ConvGemmShape& s1, const ConvGemmShape& s2, const Epilogue& e2, cudaStream_t st,
                         int sm_count);
 // fused ResBlock step for C = 32 with the fp32 activation stream in / out and block-Toeplitz ("phase form") weights
-// (conv_pair.cu): X fp32 (B,T,32); W1 phase form [64][(J+1)*32] if s1.dil == 1 else row form [32][J*32]; W2p phase form
+// (conv_pair.cu): input either X fp32 (B,T,32) (the kernel forms silu(x) itself) or S = silu(x) bf16 (B,T,32) by TMA;
+// W1 phase form [64][(J+1)*32] if s1.dil == 1 else row form [32][J*32]; W2p phase form
 bool conv_pairx_supported(const ConvGemmShape& s1, const ConvGemmShape& s2);
-int launch_conv_pairx(const float* X, const __nv_bfloat16* W1, const __nv_bfloat16* W2p, const float* bias1,
-                      const float* bias2x, const ConvGemmShape& s1, const ConvGemmShape& s2, const Epilogue& e2,
-                      cudaStream_t st, int sm_count);
+int launch_conv_pairx(const float* X, const __nv_bfloat16* S, const __nv_bfloat16* W1, const __nv_bfloat16* W2p,
+                      const float* bias1, const float* bias2x, const ConvGemmShape& s1, const ConvGemmShape& s2,
+                      const Epilogue& e2, cudaStream_t st, int sm_count);
 uint64_t conv_pairx_launch_count();
 // tap-shared 256-row-tile variant for C = N = 128 (conv_ts.cu); same operands as launch_gemm_tc
 bool conv_ts_supported(const ConvGemmShape& s);

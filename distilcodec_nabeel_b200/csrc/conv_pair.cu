@@ -25,16 +25,19 @@
 //   conv2 (dilation 1) always runs in phase form; conv1 does when its dilation is 1, else in row form (two M = 128,
 //   N = 32 blocks per tile: odd dilations never pair two outputs on one activation slice).
 //
-// Roles (832 threads, one CTA per SM, persistent over tiles of 256 t-rows -> 256 - (J-1) output rows):
+// Roles (one CTA per SM, persistent over tiles of 256 t-rows -> 256 - (J-1) output rows):
 //   warp 0        TMA: both weight sets, once
 //   warp 1        MMA issuer: conv1(i+1) is issued before conv2(i)
-//   warps 2..5    prep: x rows (fp32, global, L2-prefetched two tiles ahead) -> silu -> bf16 -> the conv1 operand tile
-//                 in the UMMA swizzled layout (zero outside the clip = conv1's padding)
-//   warps 6..9    epilogue 1: D1 -> + b1 -> silu -> bf16 -> t tile (128B-swizzled super-rows, zero outside the clip)
-//   warps 10..25  epilogue 2: four groups of 4 warps, one tile in four each: D2 -> + b2 + x (L2 hit: prep just read it)
-//                 -> x' fp32, or for the last conv of the last branch the 3-branch mean -> silu -> bf16
+//   8 warps       prep (fp32-stream form only): x rows (fp32, global, one batch of 16-byte loads per tile) -> silu ->
+//                 bf16 -> the conv1 operand tile in the UMMA swizzled layout (zero outside the clip = conv1's padding);
+//                 in the side-buffer form warp 0 loads the bf16 tile s = silu(x) by TMA instead
+//   4 warps       epilogue 1: D1 -> + b1 -> silu -> bf16 -> t tile (128B-swizzled super-rows, zero outside the clip)
+//   16 warps      epilogue 2: four groups of 4 warps, one tile in four each: D2 -> + b2 + x -> x' fp32 (+ silu(x') bf16
+//                 in the side-buffer form), or for the last conv of the last branch the 3-branch mean -> silu -> bf16
 #include "common.cuh"
 #include "ptx.cuh"
+
+#include <stdlib.h>
 
 #include "epilogue.cuh"
 
@@ -49,8 +52,11 @@ uint64_t conv_pairx_launch_count() { return g_launches_px; }
 namespace px {
 constexpr int C = 32;
 constexpr int TR = 256;                       // t rows per tile = 128 super-rows
-constexpr int PREP_WARPS = 4, E1_WARPS = 4, E2_WARPS = 16, NG2 = 4, G2W = E2_WARPS / NG2;
-constexpr int THREADS = 64 + 32 * (PREP_WARPS + E1_WARPS + E2_WARPS);
+constexpr int E1_WARPS = 4, E2_WARPS = 16, NG2 = 4, G2W = E2_WARPS / NG2;
+// PREP = 8: the operand tile is produced in the kernel from the fp32 stream (prep warps); PREP = 0: it is the bf16
+// side buffer s = silu(x) of the previous epilogue, loaded by TMA (warp 0)
+template <int PREP>
+constexpr int threads() { return 64 + 32 * (PREP + E1_WARPS + E2_WARPS); }
 constexpr int S_STAGES = 3;
 constexpr int S_ROWS = 320;                   // >= TR + (J-1)*dil = 306 (k = 11, dilation 5)
 constexpr int S_BYTES = S_ROWS * C * 2;       // 20 KB, 1024-aligned
@@ -76,11 +82,13 @@ static Layout layout(int J, bool ph1) {
 }
 }  // namespace px
 
-__global__ void __launch_bounds__(px::THREADS, 1)
+template <int PREP_WARPS>
+__global__ void __launch_bounds__(px::threads<PREP_WARPS>(), 1)
 conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                  const __grid_constant__ CUtensorMap tmS /*PREP_WARPS == 0: the bf16 operand tensor*/,
                   const float* __restrict__ x, int T, int J, int dil, int ph1 /*conv1 in phase form*/,
                   const float* __restrict__ bias1, Epilogue ep, int variant, px::Layout lay, int tiles_per_clip,
-                  int total_tiles) {
+                  int total_tiles, int dbg /*timing experiments only (DC_PAIRX_DBG): results are wrong when != 0*/) {
   using namespace px;
   constexpr uint32_t IDESC64 = ptx::make_idesc_bf16(128, 64), IDESC32 = ptx::make_idesc_bf16(128, 32);
   const int MO = TR - (J - 1), p1 = dil * (J - 1) / 2, p2 = (J - 1) / 2;
@@ -115,7 +123,7 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < S_STAGES; ++i) {
-        ptx::mbar_init(&sfull[i], PREP_WARPS);
+        ptx::mbar_init(&sfull[i], PREP_WARPS > 0 ? PREP_WARPS : 1);
         ptx::mbar_init(&sempty[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
@@ -151,6 +159,28 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         for (int j = 0; j < J; ++j) ptx::tma_load_2d(sW1 + j * W_ROW_TILE, &tmW1, wbar, j * C, 0);
       }
       for (int o = 0; o <= J; ++o) ptx::tma_load_2d(sW2 + o * W_PH_TILE, &tmW2, wbar, o * C, 0);
+      if constexpr (PREP_WARPS == 0) {
+        // the operand tiles: phase form = one box of rs/2 super-rows of the (T/2, 64) view (128B swizzle); row form =
+        // two boxes of 160 rows of the (T, 32) tensor (64B swizzle; a box dimension is limited to 256).  Rows outside
+        // the clip are zero-filled by TMA = conv1's zero padding.
+        ptx::prefetch_tmap(&tmS);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int clip = tile / tiles_per_clip, g0 = (tile % tiles_per_clip) * MO + shift_a;
+          ptx::mbar_wait(&sempty[stage], phase ^ 1);
+          uint8_t* dst = sS + stage * S_BYTES;
+          if (ph1) {
+            ptx::mbar_expect_tx(&sfull[stage], (uint32_t)((rs >> 1) * 128));
+            ptx::tma_load_3d(dst, &tmS, &sfull[stage], 0, g0 >> 1, clip);   // g0 is even in phase form (dil == 1)
+          } else {
+            ptx::mbar_expect_tx(&sfull[stage], (uint32_t)S_BYTES);
+            ptx::tma_load_3d(dst, &tmS, &sfull[stage], 0, g0, clip);
+            ptx::tma_load_3d(dst + (S_ROWS / 2) * 64, &tmS, &sfull[stage], 0, g0 + S_ROWS / 2, clip);
+          }
+          if (++stage == S_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer: conv1(0), then [conv1(i+1), conv2(i)]...
@@ -159,6 +189,7 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       const uint32_t w1_addr = ptx::smem_u32(sW1), w2_addr = ptx::smem_u32(sW2);
       int n_my = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) ++n_my;
+      const int Jm = (dbg & 32) ? 1 : J;  // timing experiment: one tap only
       int stage = 0;
       uint32_t phase = 0;
       auto conv1 = [&](int i) {
@@ -172,7 +203,7 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           const uint64_t da0 = ptx::make_smem_desc<128>(s_addr);
           const uint64_t dw0 = ptx::make_smem_desc<64>(w1_addr);
           uint32_t accum = 0;
-          for (int o = 0; o <= J; ++o) {
+          for (int o = 0; o <= Jm; ++o) {
             const uint64_t da = da0 + (uint64_t)(((o >> 1) * 128 + (o & 1) * 64) >> 4);
             const uint64_t dw = dw0 + (uint64_t)((o * W_PH_TILE) >> 4);
 #pragma unroll
@@ -188,7 +219,7 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
             uint64_t da = ptx::make_smem_desc<64>(s_addr + mb * 128 * 64);
             uint64_t dw = dw0;
             uint32_t accum = 0;
-            for (int j = 0; j < J; ++j) {
+            for (int j = 0; j < Jm; ++j) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 ptx::mma_bf16_ss(tm_d1 + b * 64 + mb * 32, da + 2 * h, dw + 2 * h, IDESC32, accum);
@@ -212,7 +243,7 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         const uint64_t dt0 = ptx::make_smem_desc<128>(ptx::smem_u32(sT + b * T_BYTES));
         const uint64_t dw0 = ptx::make_smem_desc<64>(w2_addr);
         uint32_t accum = 0;
-        for (int o = 0; o <= J; ++o) {
+        for (int o = 0; o <= Jm; ++o) {
           const uint64_t dt = dt0 + (uint64_t)(((o >> 1) * 128 + (o & 1) * 64) >> 4);
           const uint64_t dw = dw0 + (uint64_t)((o * W_PH_TILE) >> 4);
 #pragma unroll
@@ -231,24 +262,15 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       }
     }
   } else if (warp < 2 + PREP_WARPS) {
+    if constexpr (PREP_WARPS > 0) {
     // ------------------------------------------------------------ prep: x (fp32, global) -> silu -> bf16 operand tile
     const int tid = (warp - 2) * 32 + lane;            // 0..127
-    constexpr int NT = PREP_WARPS * 32, BATCH = 10;
+    constexpr int NT = PREP_WARPS * 32, BATCH = (320 * 8 + NT - 1) / NT;   // one batch of loads per tile
     const int n_f4 = rs * (C / 4);                     // float4 items of one tile: row = idx >> 3, channels 4*(idx & 7)..
     int i = 0, stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
       const int clip = tile / tiles_per_clip, o0 = (tile % tiles_per_clip) * MO;
-      {  // L2 prefetch of the rows two tiles ahead (one 128-byte line per row), so that the loads below hit L2
-        const int tile2 = tile + 2 * (int)gridDim.x;
-        if (tile2 < total_tiles) {
-          const int clip2 = tile2 / tiles_per_clip, g0 = (tile2 % tiles_per_clip) * MO + shift_a;
-          for (int r = tid; r < rs; r += NT) {
-            const int gs = g0 + r;
-            if (gs >= 0 && gs < T) prefetch_l2(x + ((size_t)clip2 * T + gs) * C);
-          }
-        }
-      }
       ptx::mbar_wait(&sempty[stage], phase ^ 1);
       uint8_t* dst = sS + stage * S_BYTES;
       const float* xc = x + (size_t)clip * T * C;
@@ -259,7 +281,7 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         for (int k = 0; k < BATCH; ++k) {
           const int idx = base + k * NT + tid;
           const int gs = g0 + (idx >> 3);
-          v[k] = (idx < n_f4 && gs >= 0 && gs < T)
+          v[k] = (idx < n_f4 && gs >= 0 && gs < T && !(dbg & 1))
                      ? __ldg(reinterpret_cast<const float4*>(xc + (size_t)gs * C) + (idx & 7))
                      : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -268,7 +290,11 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           const int idx = base + k * NT + tid;
           if (idx < n_f4) {
             const int r = idx >> 3, c4 = idx & 7;
-            const float2 lo = silu_fast2(make_float2(v[k].x, v[k].y)), hi = silu_fast2(make_float2(v[k].z, v[k].w));
+            float2 lo = make_float2(v[k].x, v[k].y), hi = make_float2(v[k].z, v[k].w);
+            if (!(dbg & 2)) {
+              lo = silu_fast2(lo);
+              hi = silu_fast2(hi);
+            }
             __nv_bfloat162 a = __floats2bfloat162_rn(lo.x, lo.y), b = __floats2bfloat162_rn(hi.x, hi.y);
             uint2 pk;
             pk.x = *reinterpret_cast<uint32_t*>(&a);
@@ -281,7 +307,7 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
             } else {    // 64B swizzle over 64-byte rows: chunk ^ ((row >> 1) & 3)
               off = r * 64 + ((chunk ^ ((r >> 1) & 3)) << 4) + sub;
             }
-            *reinterpret_cast<uint2*>(dst + off) = pk;
+            if (!(dbg & 64)) *reinterpret_cast<uint2*>(dst + off) = pk;
           }
         }
       }
@@ -289,6 +315,7 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&sfull[stage]);
       if (++stage == S_STAGES) { stage = 0; phase ^= 1; }
+    }
     }
   } else if (warp < 2 + PREP_WARPS + E1_WARPS) {
     // ------------------------------------------------------------ epilogue 1: D1 -> silu(. + b1) -> bf16 t tile in smem
@@ -318,7 +345,8 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 bb = *reinterpret_cast<const float2*>(sb1 + g * 8 + 2 * e);
-            float2 v = silu_fast2(fadd2(make_float2(__uint_as_float(acc[g * 8 + 2 * e]), __uint_as_float(acc[g * 8 + 2 * e + 1])), bb));
+            float2 v = fadd2(make_float2(__uint_as_float(acc[g * 8 + 2 * e]), __uint_as_float(acc[g * 8 + 2 * e + 1])), bb);
+            if (!(dbg & 4)) v = silu_fast2(v);
             if (!inside) v = make_float2(0.f, 0.f);
             __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
             pk[e] = *reinterpret_cast<uint32_t*>(&h);
@@ -342,7 +370,7 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     const int wg = 2 + ((warp - 2) & 3);
     float* stg = reinterpret_cast<float*>(smem + lay.stg_off) + e2w * (32 * 16);
     Epilogue epf = ep;        // prefetch only what prep has not just pulled into L2 (the mean's two other branches)
-    epf.res = nullptr;
+    if (PREP_WARPS > 0) epf.res = nullptr;
     const int T2 = T >> 1;
     int i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
@@ -352,8 +380,10 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       epilogue_prefetch(epf, clip, T2, v0 + (wg & 3) * 32, 0, 64, lane, vlim);
       ptx::mbar_wait_sleepy(&d2full[group], (uint32_t)(i / NG2) & 1u);
       ptx::tc_fence_after();
-      epilogue_tile<64, 16>(ep, variant, stg, tm_d2 + group * 64, clip, v0, 0, T2, wg, lane, vlim);
-      epilogue_tile<64, 16>(ep, variant, stg, tm_d2 + group * 64, clip, v0, 0, T2, wg + 4, lane, vlim);
+      if (!(dbg & 8)) {
+        epilogue_tile<64, 16>(ep, variant, stg, tm_d2 + group * 64, clip, v0, 0, T2, wg, lane, vlim);
+        epilogue_tile<64, 16>(ep, variant, stg, tm_d2 + group * 64, clip, v0, 0, T2, wg + 4, lane, vlim);
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&d2empty[group]);
@@ -379,14 +409,13 @@ bool conv_pairx_supported(const ConvGemmShape& s1, const ConvGemmShape& s2) {
 }
 
 // W1: conv1 weight, phase form [64][(J+1)*32] when s1.dil == 1, else row form [32][J*32]; W2p: conv2 phase form;
-// bias2x: conv2's bias repeated twice (64 floats, the two rows of a super-row).
-int launch_conv_pairx(const float* X, const __nv_bfloat16* W1, const __nv_bfloat16* W2p, const float* bias1,
-                      const float* bias2x, const ConvGemmShape& s1, const ConvGemmShape& s2, const Epilogue& e2,
-                      cudaStream_t st, int sm_count) {
+// bias2x: conv2's bias repeated twice (64 floats, the two rows of a super-row).  Exactly one of X (fp32 stream form)
+// and S (bf16 side-buffer form: S = silu(x), the residual x comes through e2.res) is given.
+template <int PREP>
+static int launch_px(const float* X, const __nv_bfloat16* S, const __nv_bfloat16* W1, const __nv_bfloat16* W2p,
+                     const float* bias1, const float* bias2x, const ConvGemmShape& s1, const Epilogue& e2,
+                     cudaStream_t st, int sm_count) {
   using namespace px;
-  DC_CHECK(conv_pairx_supported(s1, s2), DC_ERR_SHAPE, "conv_pairx: unsupported shapes");
-  DC_CHECK(X && W1 && W2p && bias1 && bias2x, DC_ERR_ARG, "conv_pairx: null operand");
-  DC_CHECK(e2.out0 != X && e2.out1 != X, DC_ERR_ARG, "conv_pairx: an output aliases the (halo-read) input");
   const int J = s1.J;
   const bool ph1 = s1.dil == 1;
   const Layout lay = layout(J, ph1);
@@ -394,14 +423,14 @@ int launch_conv_pairx(const float* X, const __nv_bfloat16* W1, const __nv_bfloat
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
   if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
-    DC_CUDA(cudaFuncSetAttribute(conv_pairx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    DC_CUDA(cudaFuncSetAttribute(conv_pairx_kernel<PREP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
   }
   const int MO = TR - (J - 1);
   const int tiles_per_clip = (s1.T + MO - 1) / MO;
   const long long total = (long long)s1.B * tiles_per_clip;
   DC_CHECK(total > 0 && total < (1ll << 31), DC_ERR_SHAPE, "conv_pairx: bad tile count");
-  CUtensorMap tmW1, tmW2;
+  CUtensorMap tmW1, tmW2, tmS;
   {
     const uint64_t K = (uint64_t)(ph1 ? J + 1 : J) * C;
     const uint64_t dims[2] = {K, (uint64_t)(ph1 ? 64 : 32)};
@@ -416,6 +445,22 @@ int launch_conv_pairx(const float* X, const __nv_bfloat16* W1, const __nv_bfloat
     const uint32_t box[2] = {(uint32_t)C, 64};
     DC_TRY(make_tmap_bf16(&tmW2, W2p, 2, dims, strides, box, 64));
   }
+  if (PREP == 0) {
+    const int rs = TR + (J - 1) * s1.dil;
+    if (ph1) {  // (B, T/2, 64) view, one box of rs/2 super-rows
+      const uint64_t dims[3] = {64, (uint64_t)(s1.T / 2), (uint64_t)s1.B};
+      const uint64_t strides[2] = {128, (uint64_t)s1.T * C * 2};
+      const uint32_t box[3] = {64, (uint32_t)(rs / 2), 1};
+      DC_TRY(make_tmap_bf16(&tmS, S, 3, dims, strides, box, 128));
+    } else {    // (B, T, 32), two boxes of S_ROWS / 2 rows
+      const uint64_t dims[3] = {(uint64_t)C, (uint64_t)s1.T, (uint64_t)s1.B};
+      const uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)s1.T * C * 2};
+      const uint32_t box[3] = {(uint32_t)C, (uint32_t)(S_ROWS / 2), 1};
+      DC_TRY(make_tmap_bf16(&tmS, S, 3, dims, strides, box, 64));
+    }
+  } else {
+    tmS = tmW2;  // unused
+  }
   Epilogue e = e2;           // the epilogue runs on the (T/2, 64) view of the (T, 32) tensors
   e.bias = bias2x;
   e.ldo = 64;
@@ -424,16 +469,31 @@ int launch_conv_pairx(const float* X, const __nv_bfloat16* W1, const __nv_bfloat
     const double rows = (double)s1.B * s1.T;
     const double macs = 2.0 * rows * C * J * C;
     const int esig = (e.res ? 4 : 0) | (e.add1 ? 8 : 0) | (e.out0 ? (e.out0_dt == DT_F32 ? 16 : 32) : 0) | (e.out1 ? 32 : 0);
-    // algorithmic bytes: x in once (the residual is the same tensor), the outputs, the mean's two other operands
-    const double out_bytes = (e.out0 ? (e.out0_dt == DT_F32 ? 4.0 : 2.0) : 0.0) + (e.out1 ? 2.0 : 0.0) + (e.add1 ? 8.0 : 0.0);
-    ProfScope ps(PC_CONV_WS, 2.0 * macs, rows * C * 4.0 + 2.0 * J * C * C * 2.0 + rows * C * out_bytes, st,
-                 "_pairx|C%d N%d J%d d%d e%d", C, C, J, s1.dil, esig);
-    conv_pairx_kernel<<<grid, THREADS, lay.total, st>>>(tmW1, tmW2, X, s1.T, J, s1.dil, ph1 ? 1 : 0, bias1, e,
-                                                        epilogue_variant(e), lay, tiles_per_clip, (int)total);
+    // algorithmic bytes: the input once (in the fp32 stream form the residual is the same tensor), the outputs, the
+    // mean's two other operands
+    const double out_bytes = (e.out0 ? (e.out0_dt == DT_F32 ? 4.0 : 2.0) : 0.0) + (e.out1 ? 2.0 : 0.0) +
+                             (e.add1 ? 8.0 : 0.0) + (PREP == 0 && e.res ? 4.0 : 0.0);
+    ProfScope ps(PC_CONV_WS, 2.0 * macs, rows * C * (PREP ? 4.0 : 2.0) + 2.0 * J * C * C * 2.0 + rows * C * out_bytes, st,
+                 PREP ? "_pairx|C%d N%d J%d d%d e%d" : "_pairs|C%d N%d J%d d%d e%d", C, C, J, s1.dil, esig);
+    static const int dbg = getenv("DC_PAIRX_DBG") ? atoi(getenv("DC_PAIRX_DBG")) : 0;
+    conv_pairx_kernel<PREP><<<grid, threads<PREP>(), lay.total, st>>>(tmW1, tmW2, tmS, X, s1.T, J, s1.dil, ph1 ? 1 : 0,
+                                                                      bias1, e, epilogue_variant(e), lay, tiles_per_clip,
+                                                                      (int)total, dbg);
   }
   ++g_launches_px;
   DC_CUDA(cudaGetLastError());
   return DC_OK;
+}
+
+int launch_conv_pairx(const float* X, const __nv_bfloat16* S, const __nv_bfloat16* W1, const __nv_bfloat16* W2p,
+                      const float* bias1, const float* bias2x, const ConvGemmShape& s1, const ConvGemmShape& s2,
+                      const Epilogue& e2, cudaStream_t st, int sm_count) {
+  DC_CHECK(conv_pairx_supported(s1, s2), DC_ERR_SHAPE, "conv_pairx: unsupported shapes");
+  DC_CHECK((X != nullptr) != (S != nullptr) && W1 && W2p && bias1 && bias2x, DC_ERR_ARG, "conv_pairx: bad operands");
+  const void* in = X ? (const void*)X : (const void*)S;
+  DC_CHECK(e2.out0 != in && e2.out1 != in, DC_ERR_ARG, "conv_pairx: an output aliases the (halo-read) input");
+  if (X) return launch_px<8>(X, nullptr, W1, W2p, bias1, bias2x, s1, e2, st, sm_count);
+  return launch_px<0>(nullptr, S, W1, W2p, bias1, bias2x, s1, e2, st, sm_count);
 }
 
 }  // namespace dc

@@ -245,12 +245,16 @@ class Pipeline:
         self._run_host(mel_host, False, codes_out, None, tiles)
         return codes_out
 
-    def tokenize_wav(self, wav_host: torch.Tensor, codes_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def tokenize_wav(self, wav_host: torch.Tensor, codes_out: Optional[torch.Tensor] = None,
+                     left_padded: bool = False) -> torch.Tensor:
         """wav -> codes entirely on the device (DistilCodec.encode with raw_audio=True, distil_codec.py:545-573 +
         :99-145) from HOST audio (B, n) fp32 at the model rate, equal lengths: left-pad by one zero sample (:134), GPU
-        log-mel (the reference runs this stage on the CPU), encoder, VQ.  Needs the engine's mel buffers."""
+        log-mel (the reference runs this stage on the CPU), encoder, VQ.  Needs the engine's mel buffers.
+        left_padded=True: `wav_host` is (B, 1 + n) and already carries the pad (what `audio.load_batch` builds)."""
         wav_host = self._pinned(wav_host)
         B, n = wav_host.shape
+        if left_padded:
+            n -= 1
         T = (n + 1 - 256) // 256 + 1
         if codes_out is None:
             codes_out = torch.empty(B, T, dtype=torch.int64, pin_memory=True)
@@ -258,8 +262,11 @@ class Pipeline:
         def upload(it):
             b0, b1 = it
             w = torch.empty(b1 - b0, n + 1, dtype=torch.float32, device=self.dev)
-            w[:, :1].zero_()                             # the reference's one-sample left pad (distil_codec.py:134)
-            self._up(w[:, 1:], wav_host[b0:b1])
+            if left_padded:
+                self._up(w, wav_host[b0:b1])
+            else:
+                w[:, :1].zero_()                         # the reference's one-sample left pad (distil_codec.py:134)
+                self._up(w[:, 1:], wav_host[b0:b1])
             return (w,)
 
         def compute(it, ins):
@@ -270,6 +277,16 @@ class Pipeline:
 
         self._run_items(self._clip_items(B, T), upload, compute, download)
         return codes_out
+
+    def tokenize_files(self, paths: Sequence[str], threads: int = 0) -> List[torch.Tensor]:
+        """Files on disk -> codes: `preprocess_audio_batch` + `encode` (distil_codec.py:146-195, 545-563) with the
+        native loader (audio.load_batch: parallel decode + resample into one pinned batch) and the GPU front-end.
+        Clip i keeps its first `n_i // 256` codes.  -> list of host int64 tensors."""
+        from . import audio
+        sr = self.eng.cfg["spec_transform"]["sampling_rate"]
+        batch, lengths, _ = audio.load_batch(list(paths), sr, threads=threads, left_pad=1, pin=True)
+        codes = self.tokenize_wav(batch, left_padded=True)
+        return [codes[i, :int(lengths[i]) // self.eng.hop].clone() for i in range(len(paths))]
 
     def tokenize_wav_ragged(self, wavs: Sequence, lengths_out: Optional[list] = None) -> List[torch.Tensor]:
         """Clips of different lengths exactly as `preprocess_raw_audio_batch` + `encode` treat them
@@ -312,6 +329,30 @@ class Pipeline:
 
         self._run_items(items, upload, compute, download)
         return wav_out
+
+    def vq_search(self, x_host: torch.Tensor, codes_out: Optional[torch.Tensor] = None, rows_per_pass: int = 8192
+                  ) -> torch.Tensor:
+        """Nearest-code search alone (EuclideanCodebook.forward eval path, vector_quantize_pytorch.py:462-538) from HOST
+        rows x (N, 3584) bf16 or fp32 to host codes (N,), in row blocks that upload while the previous block is scored."""
+        x_host = self._pinned(x_host)
+        N = x_host.shape[0]
+        if codes_out is None:
+            codes_out = torch.empty(N, dtype=torch.int64, pin_memory=True)
+        items = [(r0, min(N, r0 + rows_per_pass)) for r0 in range(0, N, rows_per_pass)]
+
+        def upload(it):
+            xb = torch.empty(it[1] - it[0], x_host.shape[1], dtype=x_host.dtype, device=self.dev)
+            self._up(xb, x_host[it[0]:it[1]])
+            return (xb,)
+
+        def compute(it, ins):
+            return (self.eng.vq_search(ins[0]),)
+
+        def download(it, outs):
+            self._down(codes_out[it[0]:it[1]], outs[0])
+
+        self._run_items(items, upload, compute, download)
+        return codes_out
 
     def decode_ragged(self, codes_list: Sequence, tails: str = "exact") -> List[torch.Tensor]:
         """Batched decode of code sequences of different lengths — what `decode_from_codes_batch` is meant to do

@@ -76,7 +76,9 @@ int dc_destroy(dc_handle h);
 /* Tunables: "vq_window" (fraction of the rigorous bf16 error bound used as the candidate window, default 0.25;
  * 1.0 = rigorous), "vq_tensor_core" (1 = tcgen05 scorer [default], 0 = CUDA-core scorer), "vq_x2_exact"
  * (0 [default] = ||x||^2 summed in the order of the reference's CPU path, ATen cascade_sum; 1 = correctly rounded),
- * "fuse_pairs" (1 [default] = the narrow decoder stages run each conv1 -> SiLU -> conv2 step as one kernel). */
+ * "fuse_pairs" (1 [default] = the narrow decoder stages run each conv1 -> SiLU -> conv2 step as one kernel),
+ * "pairx" (which fused kernel the C = 32 stage uses: 0 conv_ws_pair, 1 conv_pair on the fp32 stream, 2 [default]
+ * conv_pair with the bf16 side buffer). */
 int dc_set_option(dc_handle h, const char* key, double value);
 
 /* Weight ingestion.  Replaces `load_state_dict` on the three modules (distil_codec.py:91-94): call once per
@@ -146,6 +148,37 @@ int dc_mel_forward(dc_handle h, const float* audio_dev, int B, int Ls, float* me
  * (pinned, for the copy to be asynchronous) or device; the current device must be the one that owns the device side. */
 int dc_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
                     void* stream);
+
+/* ---- audio file I/O + resample on the host -------------------------------------------
+ * Replaces the reference's single-threaded librosa path that feeds the hot path:
+ *   load_and_resample_audio  distil_codec.py:657-684  (librosa.load(sr=None, mono=False) + librosa.resample + mean)
+ *   load_wav                 models/meldataset.py:18-20 (librosa.load(path, sr=sr)), called per clip at distil_codec.py:155
+ *   save_wav                 distil_codec.py:640-654  (soundfile.write of float32 -> 16-bit PCM)
+ * All buffers are caller-owned HOST memory (pin them to upload asynchronously); no CUDA call is made.
+ * Formats: RIFF/WAVE PCM 8/16/24/32, IEEE float 32/64, WAVE_FORMAT_EXTENSIBLE, any channel count (mono = mean).
+ * Resampler: polyphase Kaiser-windowed sinc, scipy.signal.resample_poly's design: half-length `zeros`*max(up,down)
+ * taps, Kaiser `beta`; (10, 5.0) are scipy's defaults, (32, 14.77) a high-quality setting.  Output length
+ * ceil(n*up/down).  Not bit-equal to librosa's soxr_hq: sample values only, outside the parity surface. */
+typedef struct {
+  int sample_rate, channels, bits_per_sample, is_float;
+  int64_t frames;
+} dc_audio_info;
+int dc_audio_probe(const char* path, dc_audio_info* info);
+int dc_audio_resampled_length(int64_t n_in, int sr_in, int sr_out, int64_t* n_out);
+/* threads <= 0: all host threads */
+int dc_audio_resample(const float* in, int64_t n_in, int sr_in, int sr_out, int zeros, double beta, float* out,
+                      int64_t cap, int64_t* n_out, int threads);
+/* one file -> mono float32 at target_sr (<= 0: the file's rate) of frames [frame_offset, frame_offset + max_frames)
+ * (max_frames <= 0: to the end; the `limited` crop of load_and_resample_audio); *sr_out = the rate of `out` */
+int dc_audio_load(const char* path, int target_sr, int zeros, double beta, int64_t frame_offset, int64_t max_frames,
+                  float* out, int64_t cap, int64_t* n_out, int* sr_out);
+/* n files -> rows of a (n, row_stride) float32 batch in parallel: row i = `left_pad` zeros (the reference's one-sample
+ * left pad, distil_codec.py:134), the clip, zeros to the end of the row (:133-137); lengths[i] = samples of clip i.
+ * status (nullable) receives the per-file dc_status; without it any failure fails the call. */
+int dc_audio_load_batch(const char* const* paths, int n, int target_sr, int zeros, double beta, float* out,
+                        int64_t row_stride, int64_t left_pad, int64_t* lengths, int* status, int threads);
+/* mono float32 in [-1, 1] -> 16-bit PCM WAV with libsndfile's float conversion (scale 0x8000, round, clip) */
+int dc_audio_write_wav(const char* path, const float* data, int64_t n, int sample_rate);
 
 /* Layout helpers between the reference's channels-first tensors and the ABI's channels-last ones. */
 int dc_ncl_to_nlc(const float* in_dev, float* out_dev, int B, int C, int T, void* stream);

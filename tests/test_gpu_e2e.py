@@ -296,17 +296,16 @@ def test_fp32_stream_pair_kernel_matches_oracle_and_the_two_kernel_form(variant)
         z = make_latents(B, T, seed=seed) * 0.5
         ref = R.generator_forward(sd, z)[:, 0]
         zd = z.transpose(1, 2).contiguous().to(eng.device)
+        outs, counts = {}, {}
         try:
-            eng.set_option("pairx", 1)
-            n0 = eng.launch_count()
-            wav_new = eng.generator(zd)
-            n_new = eng.launch_count() - n0
-            eng.set_option("pairx", 0)
-            n0 = eng.launch_count()
-            wav_old = eng.generator(zd)
-            n_old = eng.launch_count() - n0
+            for form in (0, 1, 2):      # conv_ws_pair | conv_pair on the fp32 stream | conv_pair on the bf16 side buffer
+                eng.set_option("pairx", form)
+                n0 = eng.launch_count()
+                outs[form] = eng.generator(zd)
+                counts[form] = eng.launch_count() - n0
         finally:
-            eng.set_option("pairx", 1)
-        assert n_new == n_old                                   # one launch per ResBlock step either way
-        assert rel_err(wav_new, ref) < TOL["bf16"], (B, T)
-        assert rel_err(wav_new, wav_old) < 2e-4, (B, T)          # only the summation order differs
+            eng.set_option("pairx", 2)
+        assert counts[0] == counts[1] == counts[2]              # one launch per ResBlock step in every form
+        for form in (1, 2):
+            assert rel_err(outs[form], ref) < TOL["bf16"], (B, T, form)
+            assert rel_err(outs[form], outs[0]) < 2e-4, (B, T, form)   # only the summation order differs

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.conftest import golden, rel_err, state_dict
+from tests.conftest import engine, golden, rel_err, state_dict
 
 pytestmark = pytest.mark.gpu
 
@@ -108,3 +108,60 @@ def test_bulk_encode_on_the_device(codec):
             assert torch.equal(ret.quantized_fup_list[b],
                                want.quantized_fup[b, :h].reshape(h, 2, -1).reshape(h * 2, -1).cpu())
             assert not ret.x_pjt_in_list[b].is_cuda and ret.x_pjt_in_list[b].shape == (2 * h, 1792)
+
+
+def test_ragged_batched_decode_and_tokenize():
+    """Row f-3: per-clip lengths.  decode_ragged(tails="padded") = each clip's row of the
+    right-padded batch, i.e. `decode_from_codes` of the padded sequence (what the reference's batch method is meant
+    to return, distil_codec.py:598-639); tails="exact" = `decode_from_codes(codes_i)` of the clip alone, bit for bit
+    (the shorter clips' last frames re-decoded from a tile that ends at the clip's own end).  tokenize_wav_ragged pads
+    the AUDIO like preprocess_raw_audio_batch (distil_codec.py:133-137) and crops to n_i // 256 codes."""
+    from distilcodec_nabeel_b200.sharding import Pipeline
+    from tests.golden.inputs import make_wav
+    eng = engine("W1", "bf16")
+    pipe = Pipeline(eng)
+    g = torch.Generator().manual_seed(11)
+    lens = [300, 17, 129, 300, 1, 95]
+    seqs = [torch.randint(0, 32768, (n,), generator=g) for n in lens]
+    alone = [pipe.decode(s[None].contiguous())[0] for s in seqs]
+    exact = pipe.decode_ragged(seqs, tails="exact")
+    padded = pipe.decode_ragged(seqs, tails="padded")
+    for i, n in enumerate(lens):
+        assert exact[i].shape == padded[i].shape == (256 * n,)
+        assert torch.equal(exact[i], alone[i]), i                              # length-mask semantics, bit-exact
+        pad = torch.zeros(max(lens), dtype=torch.int64)
+        pad[:n] = seqs[i]
+        assert torch.equal(padded[i], pipe.decode(pad[None].contiguous())[0, :256 * n]), i
+        keep = max(0, n - 48) * 256                                           # the two differ only in the clip's tail
+        assert torch.equal(exact[i][:keep], padded[i][:keep])
+    wavs = [make_wav(1, n, seed=20 + k)[0] for k, n in enumerate([256 * 40 + 100, 256 * 12, 256 * 40 - 1])]
+    out_lens = []
+    codes = pipe.tokenize_wav_ragged(wavs, out_lens)
+    assert out_lens == [40, 12, 39] and [int(c.numel()) for c in codes] == out_lens
+    mx = max(int(w.numel()) for w in wavs)
+    for i, w in enumerate(wavs):
+        padded_w = torch.zeros(1, mx)
+        padded_w[0, :w.numel()] = w
+        assert torch.equal(codes[i], pipe.tokenize_wav(padded_w.pin_memory())[0, :out_lens[i]])
+
+
+def test_strided_dma_copies_and_host_vq_search():
+    """dc_copy2d_async: time tiles / per-clip crops move between PINNED host tensors and the device without staging."""
+    from distilcodec_nabeel_b200.sharding import Pipeline
+    from tests.golden.inputs import make_vq_rows
+    eng = engine("W1", "bf16")
+    pipe = Pipeline(eng)
+    host = torch.arange(3 * 128 * 50, dtype=torch.float32).reshape(3, 128, 50).pin_memory()
+    dev = torch.empty(2, 128, 20, device=eng.device)
+    pipe._copy2d(dev, host[1:3, :, 7:27], pipe.copy_stream)
+    pipe.copy_stream.synchronize()
+    assert torch.equal(dev.cpu(), host[1:3, :, 7:27])
+    back = torch.zeros(3, 128, 50).pin_memory()
+    pipe._copy2d(back[0:2, :, 30:50], dev, pipe.copy_stream)
+    pipe.copy_stream.synchronize()
+    assert torch.equal(back[0:2, :, 30:50], host[1:3, :, 7:27]) and float(back[2].abs().sum()) == 0.0
+    with pytest.raises(ValueError):
+        pipe._copy2d(dev, torch.zeros(2, 128, 20), pipe.copy_stream)             # pageable host memory is refused
+    x = make_vq_rows(3000, kind="bf16", seed=8).to(torch.bfloat16)
+    c_host = pipe.vq_search(x.pin_memory(), rows_per_pass=1024)
+    assert torch.equal(c_host, eng.vq_search(x.to(eng.device)).cpu())
