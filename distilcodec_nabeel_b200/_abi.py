@@ -52,6 +52,7 @@ SIGNATURES = {
     "dc_workspace_bytes": (_i, [_vp, _i, _i, _i, C.POINTER(_sz)]),
     "dc_encoder_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "dc_quantizer_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dc_quantizer_encode": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "dc_vq_search": (_i, [_vp, _vp, _i, _vp, _i64, _vp, _vp, _sz, _vp, C.POINTER(_i)]),
     "dc_vq_workspace_bytes": (_i, [_vp, _i64, _i, C.POINTER(_sz)]),
     "dc_quantizer_decode": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),

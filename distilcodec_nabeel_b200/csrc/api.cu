@@ -513,9 +513,12 @@ static int stage_quantizer(const dc_handle_s* h, const float* enc, int B, int T,
   void* a = ar.get(rows * D * es);
   void* hid = ar.get(rows * D * 4 * es);
   void* zop = ar.get(rows * D * es);
-  void* qd = ar.get(rows * D * es);
+  // codes only (DownsampleGRVQ.encode, grfvq.py:134-139): no codebook gather, no project_out / upsample tail
+  const bool codes_only = !dry && quantized == nullptr;   // the workspace plan (dry) covers the full forward
+  void* qd = codes_only ? nullptr : ar.get(rows * D * es);
   void* enc_op = h->mode == DC_MODE_BF16 ? ar.get(rows * D * 2) : nullptr;
-  void* fup_op = (h->mode == DC_MODE_BF16 || !fup) ? ar.get(rows * CD * es) : nullptr;
+  void* fup_op = (!codes_only && (h->mode == DC_MODE_BF16 || !fup)) ? ar.get(rows * CD * es) : nullptr;
+  void* xin_tmp = (x_pjt_in && !dry) ? nullptr : ar.get(rows * CD * es);  // project_in rows: scratch if the caller does not want them
   const size_t vq_bytes = vq_workspace_bytes((int64_t)rows, CD, ad == DT_BF16);
   void* vq_ws = ar.get(vq_bytes);
   if (dry) return DC_OK;
@@ -532,6 +535,7 @@ static int stage_quantizer(const dc_handle_s* h, const float* enc, int B, int T,
     DC_TRY(run_dense(h, h->q_down, a0, B, T, e, st));
     DC_TRY(run_block(h, h->q_down_blk, x, a, hid, B, T, nullptr, zop, false, st));
   }
+  if (!x_pjt_in) x_pjt_in = xin_tmp;
   {  // project_in (residual_vq.py:152); output dtype = what the reference hands to the codebook
     Epilogue e;
     e.out0 = x_pjt_in;
@@ -540,6 +544,7 @@ static int stage_quantizer(const dc_handle_s* h, const float* enc, int B, int T,
   }
   DC_TRY(launch_vq_search(x_pjt_in, ad, nullptr, (int64_t)rows, CD, h->codebook, h->codebook_bf16, h->c2, h->c2max,
                           h->K, codes, vq_ws, vq_bytes, h->vq_window, h->vq_tc, h->vq_x2_exact, st, h->sm_count, nullptr));
+  if (codes_only) return DC_OK;
   // batched_embedding (vector_quantize_pytorch.py:243-247,506): quantized_fup = codebook rows
   const void* fop;
   if (h->mode == DC_MODE_BF16) {
@@ -1132,6 +1137,11 @@ int dc_quantizer_forward(dc_handle h, const float* enc_nlc_dev, int B, int T, in
   DC_CHECK(x_pjt_in_dev != nullptr && quantized_nlc_dev != nullptr, DC_ERR_ARG, "null output pointer");
   return run_stage(h, DC_STAGE_QUANTIZER, B, T, enc_nlc_dev, codes_dev, x_pjt_in_dev, fup_dev, quantized_nlc_dev, ws_dev,
                    ws_bytes, stream);
+}
+
+int dc_quantizer_encode(dc_handle h, const float* enc_nlc_dev, int B, int T, int64_t* codes_dev, void* ws_dev,
+                        size_t ws_bytes, void* stream) {
+  return run_stage(h, DC_STAGE_QUANTIZER, B, T, enc_nlc_dev, codes_dev, nullptr, nullptr, nullptr, ws_dev, ws_bytes, stream);
 }
 
 int dc_quantizer_decode(dc_handle h, const int64_t* codes_dev, int B, int T, float* z_nlc_dev, void* ws_dev,

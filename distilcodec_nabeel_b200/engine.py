@@ -185,6 +185,22 @@ class Engine:
                     quant[b0:b0 + b].data_ptr(), ws.data_ptr(), ws.numel(), self._stream()), "dc_quantizer_forward")
         return codes, xin, fup, quant
 
+    def quantizer_encode(self, enc_nlc: torch.Tensor) -> torch.Tensor:
+        """latents (B, T, 1024) fp32 -> codes (B, T) int64 only (DownsampleGRVQ.encode, grfvq.py:134-139): skips the
+        codebook gather and the project_out / upsample tail of the full forward."""
+        self._check_in(enc_nlc, torch.float32, (self.latent_dim,))
+        B, T, _ = enc_nlc.shape
+        codes = torch.empty(B, T, dtype=torch.int64, device=self.device)
+        step = self.clips_per_call(_abi.STAGE_QUANTIZER, B, T)
+        with torch.cuda.device(self.device):
+            for b0 in range(0, B, step):
+                b = min(step, B - b0)
+                ws = self._workspace(self.workspace_bytes(_abi.STAGE_QUANTIZER, b, T))
+                _abi.check(self.lib.dc_quantizer_encode(self.h, enc_nlc[b0:b0 + b].data_ptr(), b, T,
+                                                        codes[b0:b0 + b].data_ptr(), ws.data_ptr(), ws.numel(),
+                                                        self._stream()), "dc_quantizer_encode")
+        return codes
+
     def decode_codes(self, codes: torch.Tensor) -> torch.Tensor:
         """codes (B, T) int64 -> z (B, T, 1024) fp32.  grfvq.py:141-146."""
         self._check_in(codes, torch.int64)

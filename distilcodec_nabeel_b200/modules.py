@@ -167,8 +167,7 @@ class B200Quantizer(_Shim):
     def encode(self, z: torch.Tensor) -> torch.Tensor:
         """grfvq.py:134-139: (B,1024,T) -> codes (B, G*R = 1, T)."""
         eng = self._engines.get()
-        codes, _, _, _ = eng.quantizer(eng.ncl_to_nlc(self._dev(z).float()), want_fup=False)
-        return codes.unsqueeze(1)
+        return eng.quantizer_encode(eng.ncl_to_nlc(self._dev(z).float())).unsqueeze(1)
 
     @torch.no_grad()
     def decode(self, indices: torch.Tensor) -> torch.Tensor:

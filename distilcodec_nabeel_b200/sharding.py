@@ -110,9 +110,12 @@ class Pipeline:
         return self.eng.clips_per_call(_abi.STAGE_GENERATOR, B, T)
 
     # ---- device-resident legs (used by bench.py's kernel-only timing) --------------------------------------
-    def encode_device(self, mel_dev: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """mel (B,128,T) on device -> (codes (B,T) int64, quantized (B,T,1024) fp32) on device."""
+    def encode_device(self, mel_dev: torch.Tensor, codes_only: bool = False):
+        """mel (B,128,T) on device -> (codes (B,T) int64, quantized (B,T,1024) fp32) on device.  codes_only: the
+        tokenisation legs stop at the search (quantizer.encode, grfvq.py:134-139) and return (codes, None)."""
         enc = self.eng.encoder(mel_dev)
+        if codes_only:
+            return self.eng.quantizer_encode(enc), None
         codes, _, _, quant = self.eng.quantizer(enc, want_fup=False)
         return codes, quant
 
@@ -127,7 +130,7 @@ class Pipeline:
 
     def tokenize_wav_device(self, wav_padded_dev: torch.Tensor) -> torch.Tensor:
         """audio (B, n+1) on device, already left-padded by one zero sample (distil_codec.py:134) -> codes (B,T)."""
-        return self.encode_device(self.eng.mel(wav_padded_dev))[0]
+        return self.encode_device(self.eng.mel(wav_padded_dev), codes_only=True)[0]
 
     # ---- the copy / compute pipeline ----------------------------------------------------------------------
     def _copy2d(self, dst: torch.Tensor, src: torch.Tensor, stream: torch.cuda.Stream) -> int:
@@ -216,7 +219,7 @@ class Pipeline:
         def compute(it, ins):
             if want_wav:
                 return self.reconstruct_device(ins[0])
-            return (self.encode_device(ins[0])[0],)
+            return (self.encode_device(ins[0], codes_only=True)[0],)
 
         def download(it, outs):
             b0, b1, lo, hi, s, e = it
@@ -439,7 +442,7 @@ def tokenize_long_device(pipe: "Pipeline", mel_dev: torch.Tensor, tile: int = 81
     step = pipe._chunk(B, min(T, tile + 2 * ENCODE_HALO))
     for lo, hi, s, e in time_tiles(T, tile, ENCODE_HALO):
         for b0 in range(0, B, step):
-            c, _ = pipe.encode_device(mel_dev[b0:b0 + step, :, lo:hi].contiguous())
+            c, _ = pipe.encode_device(mel_dev[b0:b0 + step, :, lo:hi].contiguous(), codes_only=True)
             codes[b0:b0 + step, s:e] = c[:, s - lo:e - lo]
     return codes
 

@@ -108,6 +108,13 @@ int dc_encoder_forward(dc_handle h, const float* mel_ncl_dev, int B, int T, floa
 int dc_quantizer_forward(dc_handle h, const float* enc_nlc_dev, int B, int T, int64_t* codes_dev, void* x_pjt_in_dev,
                          float* fup_dev, float* quantized_nlc_dev, void* ws_dev, size_t ws_bytes, void* stream);
 
+/* quantizer.encode(enc): DownsampleGRVQ.encode, grfvq.py:134-139 — the codes alone (what a tokenisation job keeps of
+ * `DistilCodec.encode`, distil_codec.py:545-563): downsample + project_in + search; no codebook gather, no project_out /
+ * upsample tail, no x_pjt_in / quantized_fup stores.  Same workspace requirement as dc_quantizer_forward.
+ *   enc_nlc_dev : fp32 (B, T, 1024);  codes_dev : int64 (B, T) */
+int dc_quantizer_encode(dc_handle h, const float* enc_nlc_dev, int B, int T, int64_t* codes_dev, void* ws_dev,
+                        size_t ws_bytes, void* stream);
+
 /* Nearest-code search only: EuclideanCodebook.forward eval path, vector_quantization/utils/
  * vector_quantize_pytorch.py:462-538 (cdist :41-45, argmax :96).  Returns exactly
  *   argmax_j -sqrt(max((x2 + c2_j) + (-2 * x.c_j), 0))   with the lowest index on ties,

@@ -33,6 +33,9 @@ class OracleEngine:
         q = R.quantizer_forward(self.sd, enc_nlc.transpose(1, 2))
         return q["codes"][0, :, :, 0], q["x_pjt_in"], q["quantized_fup"], q["quantized"].transpose(1, 2).contiguous()
 
+    def quantizer_encode(self, enc_nlc):
+        return self.quantizer(enc_nlc, want_fup=False)[0]
+
     def decode_codes(self, codes):
         return R.quantizer_decode(self.sd, codes[None, :, :, None]).transpose(1, 2).contiguous()
 

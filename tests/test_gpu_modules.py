@@ -165,3 +165,25 @@ def test_strided_dma_copies_and_host_vq_search():
     x = make_vq_rows(3000, kind="bf16", seed=8).to(torch.bfloat16)
     c_host = pipe.vq_search(x.pin_memory(), rows_per_pass=1024)
     assert torch.equal(c_host, eng.vq_search(x.to(eng.device)).cpu())
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_codes_only_quantizer_encode_equals_the_full_forward(mode):
+    """dc_quantizer_encode (DownsampleGRVQ.encode, grfvq.py:134-139) skips the gather and the project_out / upsample
+    tail; the codes are those of the full forward, bit for bit, and the shim's `encode` has the reference's layout."""
+    from distilcodec_nabeel_b200 import build_modules
+    from tests.golden.inputs import make_latents
+    eng = engine("W1", mode)
+    enc = make_latents(3, 77, seed=44).transpose(1, 2).contiguous().to(eng.device)
+    n0 = eng.launch_count()
+    codes_full = eng.quantizer(enc, want_fup=False)[0]
+    n_full = eng.launch_count() - n0
+    n0 = eng.launch_count()
+    codes = eng.quantizer_encode(enc)
+    n_codes = eng.launch_count() - n0
+    assert torch.equal(codes, codes_full) and codes.dtype == torch.int64 and codes.shape == (3, 77)
+    assert n_codes < n_full                                                   # fewer kernels: no gather, no tail
+    _, q, _ = build_modules(state_dict("W1"), eng.device, force_mode=mode)
+    out = q.encode(enc.transpose(1, 2))
+    assert out.shape == (3, 1, 77) and torch.equal(out[:, 0], codes)
+    q._engines.invalidate()
