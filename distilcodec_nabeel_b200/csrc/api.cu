@@ -151,7 +151,7 @@ struct dc_handle_s {
   bool finalized = false;
   std::map<std::string, RawTensor> raw;
   std::vector<void*> owned;
-  float vq_window = 0.25f;
+  float vq_window = 1.0f;
   bool vq_tc = true;
   bool vq_x2_exact = false;
   bool fuse_pairs = true;
@@ -989,6 +989,7 @@ int dc_finalize(dc_handle h, void* stream) {
     }
     ++g_launches_api;
     DC_CUDA(cudaGetLastError());
+    DC_TRY(launch_vq_resid_max(cb->d, h->K, h->CD, h->c2max + 1, st));   // max ||c - bf16(c)||^2 for the search window
   }
 
   if (has_gen) {  // ---- generator (models/generators.py:29-116)

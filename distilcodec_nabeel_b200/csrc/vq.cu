@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) vq_prep_kernel(const void* __restrict__ x
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
-  float x2;
+  float x2, dx2 = 0.f;   // dx2 = ||x - bf16(x)||^2 (0 when x already is bf16)
   if constexpr (X_BF16) {
     const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(x) + (size_t)row * D;
     if (x2_exact) {
@@ -161,7 +161,15 @@ __global__ void __launch_bounds__(256) vq_prep_kernel(const void* __restrict__ x
   } else {
     const float* p = reinterpret_cast<const float*>(x) + (size_t)row * D;
     __nv_bfloat16* o = xb + (size_t)row * D;
-    for (int i = lane; i < D; i += 32) o[i] = __float2bfloat16_rn(__ldg(p + i));
+    for (int i = lane; i < D; i += 32) {
+      const float v = __ldg(p + i);
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      o[i] = b;
+      const float d = v - __bfloat162float(b);   // exact (Sterbenz): the rounding residual of this element
+      dx2 = fmaf(d, d, dx2);
+    }
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) dx2 += __shfl_xor_sync(0xffffffffu, dx2, o2);
     if (x2_exact) {
       double s = 0.0;
       for (int i = lane; i < D; i += 32) {
@@ -176,11 +184,17 @@ __global__ void __launch_bounds__(256) vq_prep_kernel(const void* __restrict__ x
     }
   }
   if (lane == 0) {
-    const float c2max = *c2max_p;
-    const float xn = sqrtf(x2), cn = sqrtf(c2max);
-    // unit roundoff of bf16 is 2^-8 per rounded operand; fp32 accumulation over D terms adds at most D * 2^-23
-    const float u = (X_BF16 ? 1.f : 2.f) * 0.00390625f + (float)D * 1.1920929e-7f;
-    const float e = 2.f * u * xn * cn;                  // |S_bf16 - S_exact| <= e  (S = c2 - 2 x.c)
+    // Candidate window of the bf16 tensor-core scorer.  S~_j = c2_j - 2 <x~, c~_j> (x~, c~ = bf16 roundings, fp32
+    // accumulate) differs from the exact s_j = c2_j - 2 <x, c_j> by 2 (<x - x~, c_j> + <x~, c_j - c~_j>) + accumulation,
+    // so by Cauchy-Schwarz   |S~_j - s_j| <= e := 2 (||x - x~|| ||c||max + ||x~|| ||c - c~||max) + e_acc
+    // with the EXACT rounding-residual norms: ||x - x~|| of this row (above) and max_j ||c_j - c~_j|| of the codebook
+    // (dc_finalize).  Those are ~0.3 of the generic 2^-8 |v| bound, which is why a window of 2 e is both rigorous and
+    // small enough for the 32-slot candidate lists on every weight set of the tests.  window_factor scales it
+    // (option "vq_window", 1.0 = this bound); 6 ulp(d^2) cover the fp32 evaluation of the reference's own expression.
+    const float c2max = c2max_p[0], r2max = c2max_p[1];
+    const float xn = sqrtf(x2) * 1.0001f, cn = sqrtf(c2max), dx = sqrtf(dx2) * 1.001f, rn = sqrtf(r2max) * 1.001f;
+    const float e_acc = 2.f * (float)D * 1.1920929e-7f * xn * cn;   // fp32 accumulation over D products
+    const float e = 2.f * (dx * cn + xn * rn) + e_acc;
     const float dmax2 = x2 + c2max + 2.f * xn * cn;     // upper bound of the reference's d^2
     int ex = 0;
     frexpf(fmaxf(dmax2, 1e-30f), &ex);                  // dmax2 = m * 2^ex, m in [0.5, 1)
@@ -188,6 +202,34 @@ __global__ void __launch_bounds__(256) vq_prep_kernel(const void* __restrict__ x
     x2e[row] = x2;
     win[row] = window_factor * 2.f * e + 6.f * ulp;
   }
+}
+
+// max_j ||c_j - bf16(c_j)||^2 of the codebook (dc_finalize): the second factor of the candidate-window bound above.
+// out must be zeroed; non-negative floats order like their bit patterns.
+__global__ void __launch_bounds__(256) vq_resid_max_kernel(const float* __restrict__ cb, int64_t rows, int D,
+                                                           float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* p = cb + (size_t)row * D;
+  float s = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float v = __ldg(p + i);
+    const float d = v - __bfloat162float(__float2bfloat16_rn(v));
+    s = fmaf(d, d, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(s));
+}
+int launch_vq_resid_max(const float* cb, int64_t rows, int D, float* out, cudaStream_t st) {
+  DC_CUDA(cudaMemsetAsync(out, 0, 4, st));
+  if (rows == 0) return DC_OK;
+  ProfScope ps(PC_PREPACK, 0, 0, st);
+  vq_resid_max_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(cb, rows, D, out);
+  ++g_launches_vq;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
 }
 
 // ||c_j||^2 of the codebook in the same ATen order (`(y ** 2).sum(-1)`, vector_quantize_pytorch.py:43)

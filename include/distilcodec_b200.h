@@ -73,8 +73,9 @@ int dc_default_config(dc_config* cfg);
 /* Lifetime.  Replaces module construction + `.to(device)` (distil_codec.py:52-54, 72-75).  cfg NULL = defaults. */
 int dc_create(int device, int mode, const dc_config* cfg, dc_handle* out);
 int dc_destroy(dc_handle h);
-/* Tunables: "vq_window" (fraction of the rigorous bf16 error bound used as the candidate window, default 0.25;
- * 1.0 = rigorous), "vq_tensor_core" (1 = tcgen05 scorer [default], 0 = CUDA-core scorer), "vq_x2_exact"
+/* Tunables: "vq_window" (scale of the candidate window of the bf16 tensor-core scorer; 1.0 [default] = the rigorous
+ * bound built from the exact rounding-residual norms of the row and of the codebook, so the exact winner always
+ * survives to the fp32 re-score), "vq_tensor_core" (1 = tcgen05 scorer [default], 0 = CUDA-core scorer), "vq_x2_exact"
  * (0 [default] = ||x||^2 summed in the order of the reference's CPU path, ATen cascade_sum; 1 = correctly rounded),
  * "fuse_pairs" (1 [default] = the narrow decoder stages run each conv1 -> SiLU -> conv2 step as one kernel),
  * "pairx" (which fused kernel the C = 32 stage uses: 0 conv_ws_pair, 1 conv_pair on the fp32 stream, 2 [default]

@@ -110,10 +110,11 @@ def test_w0_end_to_end_code_agreement(mode):
 
 
 def test_near_tie_rows_resolve_exactly_with_the_default_window():
-    """Adversarial rows for the tensor-core scorer's candidate window ("vq_window", a quarter of the rigorous bf16 error
-    bound by default): x sits between two codebook rows, displaced towards one of them by a relative 1e-7 .. 1e-2 of
-    their distance, so the two exact distances differ by far less than the bf16 scoring error.  The exact winner must
-    survive the window and win the fp32 re-score: identical to the oracle, and identical to the rigorous window."""
+    """Adversarial rows for the tensor-core scorer's candidate window ("vq_window" 1.0 = the rigorous bound from the exact
+    bf16 rounding-residual norms of the row and of the codebook, csrc/vq.cu): x sits between two codebook rows, displaced
+    towards one of them by a relative 1e-7 .. 1e-2 of their distance, so the two exact distances differ by far less than
+    the bf16 scoring error.  The exact winner must survive the window and win the fp32 re-score: identical to the oracle,
+    identical to a window four times as wide, and (the bound is not tight) still identical at a quarter of it."""
     sd = state_dict("W1")
     eng = engine("W1", "bf16")
     E = sd[CODEBOOK][0]
@@ -131,12 +132,15 @@ def test_near_tie_rows_resolve_exactly_with_the_default_window():
             xd = xd.to(torch.bfloat16)
         ref = R.vq_search(xk, E)
         got, st = eng.vq_search(xd.contiguous(), stats=True)
-        eng.set_option("vq_window", 1.0)
         try:
+            eng.set_option("vq_window", 4.0)
             rig = eng.vq_search(xd.contiguous())
-        finally:
             eng.set_option("vq_window", 0.25)
-        assert torch.equal(got, rig), kind                       # the default window loses nothing on these rows
+            quarter = eng.vq_search(xd.contiguous())
+        finally:
+            eng.set_option("vq_window", 1.0)
+        assert torch.equal(got, rig) and torch.equal(got, quarter), kind
+        assert st["exhaustive_rows"] == 0
         # vs the oracle: exact fp32 ties may be broken differently only through torch's CPU sqrt (not correctly
         # rounded): at most a couple of rows, and only at vanishing gaps
         bad = (got.cpu() != ref).nonzero().reshape(-1)

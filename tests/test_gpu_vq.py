@@ -33,7 +33,10 @@ def test_golden_indices(variant, kind, mode):
     codes = codes.cpu().numpy()
     ref = g[f"codes_{kind}"]
     _check_gate(codes, ref, g[f"gap_{kind}"])
-    assert st["rows"] == 4096 and st["exhaustive_rows"] == 0
+    # candidate lists (32 slots x splits) hold every row whose x is bf16-representable; with full-precision rows the
+    # rigorous window also has to cover the rounding of x itself and ~1 % of the W0 rows overflow into the exhaustive
+    # exact pass (same result, by construction)
+    assert st["rows"] == 4096 and st["exhaustive_rows"] <= (0 if kind == "bf16" else 130)
     # W0 is the hard case: candidates collapse onto the fp32 rounding grid and 3.7 % of rows tie exactly.  With
     # ||x||^2 summed in ATen's order the kernel reproduces the reference except where torch's CPU sqrt (MKL VML,
     # not correctly rounded: e.g. sqrt(650.2907104492188f) -> 25.500797 where IEEE gives 25.500799) breaks a tie
@@ -53,19 +56,19 @@ def test_tensor_core_and_cuda_core_scorers_agree():
     assert torch.equal(a, b)
 
 
-def test_caller_supplied_x2_and_rigorous_window():
-    """x2 computed by the caller's reference (here torch CPU) and the rigorous (factor 1.0) candidate window.  On W0
-    the rigorous bf16 error bound admits more than the 256 list slots per row, so this also covers pass 3 (the
-    exhaustive exact scan of overflowed rows)."""
+def test_caller_supplied_x2_and_overflowing_window():
+    """x2 computed by the caller's reference (here torch CPU) and a candidate window 8x the rigorous bound.  On W0 that
+    admits more than the 256 list slots per row, so this also covers pass 3 (the exhaustive exact scan of overflowed
+    rows)."""
     g = golden("vq_W0.npz")
     eng = engine("W0", "fp32")
     x = make_vq_rows(4096, kind="fp32")[:1500]
     x2 = (x ** 2).sum(-1)
-    eng.set_option("vq_window", 1.0)
+    eng.set_option("vq_window", 8.0)
     try:
         codes, st = eng.vq_search(x.to(eng.device), x2.to(eng.device), stats=True)
     finally:
-        eng.set_option("vq_window", 0.25)
+        eng.set_option("vq_window", 1.0)
     assert np.array_equal(codes.cpu().numpy(), g["codes_fp32"][:1500])
     assert st["exhaustive_rows"] > 0
 
