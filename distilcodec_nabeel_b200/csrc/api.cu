@@ -403,7 +403,10 @@ static int run_conv_pair(const dc_handle_s* h, const Dense& c1, const Dense& c2,
   ConvGemmShape s2{B, T, c2.C, c2.J, c2.shift0, c2.dil, c2.N, c2.alg_scale, c2.phase_cols, c2.zero_taps};
   if (pair_fuses(h, c1, c2, B, T)) {
     DC_CHECK(e2.out1 != S && e2.out0 != S, DC_ERR_ARG, "fused conv pair: an output aliases the activation input");
-    if (h->pairx == 2 && conv_pairx_supported(s1, s2) && c2.w_phase && c2.bias2x && (c1.dil != 1 || c1.w_phase)) {
+    // conv_pair.cu (phase-form MMAs) for the plain residual steps; the step that folds the 3-branch mean reads 14 B per
+    // element in its epilogue and measured faster on conv_ws_pair's smaller tiles (6.4 vs 8.8 ms at 256 x 10 s)
+    if (h->pairx == 2 && !e2.add1 && conv_pairx_supported(s1, s2) && c2.w_phase && c2.bias2x &&
+        (c1.dil != 1 || c1.w_phase)) {
       e2.prefetch = h->epi_prefetch;
       return launch_conv_pairx(nullptr, reinterpret_cast<const __nv_bfloat16*>(S), c1.dil == 1 ? c1.w_phase : c1.w_bf16,
                                c2.w_phase, c1.bias, c2.bias2x, s1, s2, e2, st, h->sm_count);

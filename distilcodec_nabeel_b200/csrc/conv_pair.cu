@@ -52,24 +52,37 @@ uint64_t conv_pairx_launch_count() { return g_launches_px; }
 namespace px {
 constexpr int C = 32;
 constexpr int TR = 256;                       // t rows per tile = 128 super-rows
-constexpr int E1_WARPS = 4, E2_WARPS = 16, NG2 = 4, G2W = E2_WARPS / NG2;
+#ifndef DC_PX_NG2
+#define DC_PX_NG2 3   // epilogue-2 groups of the side-buffer form (A/B on one B200: 4 and 6 groups time the same)
+#endif
+#ifndef DC_PX_CW
+// Epilogue-2 transpose chunk width of the side-buffer form.  32 columns = every global access of a warp is whole
+// 128-byte lines; with 16 (64-byte half lines) ncu showed the LSU data pipe 82 % busy at 1.3 sectors per wavefront, which
+// under the power-capped clock of the full step is what bounds the kernel (it is HBM-bound, 6.15 TB/s, at 1.75 GHz).
+// A/B: 40.4-42.1 -> 37.8-38.3 ms per step.  The 4 KB per warp this needs is paid for with 3 groups and a 2-deep tile ring.
+#define DC_PX_CW 32
+#endif
+constexpr int E1_WARPS = 4, G2W = 4;
+constexpr int cw(int prep) { return prep ? 16 : DC_PX_CW; }
+constexpr int ng2(int prep) { return prep ? 4 : DC_PX_NG2; }      // epilogue-2 groups (one D2 accumulator each)
+constexpr int e2_warps(int prep) { return G2W * ng2(prep); }
+constexpr int s_stages(int prep) { return (ng2(prep) > 4 || cw(prep) > 16) ? 2 : 3; }  // operand-tile ring depth (smem budget)
 // PREP = 8: the operand tile is produced in the kernel from the fp32 stream (prep warps); PREP = 0: it is the bf16
 // side buffer s = silu(x) of the previous epilogue, loaded by TMA (warp 0)
 template <int PREP>
-constexpr int threads() { return 64 + 32 * (PREP + E1_WARPS + E2_WARPS); }
-constexpr int S_STAGES = 3;
+constexpr int threads() { return 64 + 32 * (PREP + E1_WARPS + e2_warps(PREP)); }
 constexpr int S_ROWS = 320;                   // >= TR + (J-1)*dil = 306 (k = 11, dilation 5)
 constexpr int S_BYTES = S_ROWS * C * 2;       // 20 KB, 1024-aligned
 constexpr int T_BYTES = 136 * 128;            // 128 super-rows + the (J+1)/2 <= 6 the last offsets touch, 1024-aligned
 constexpr int W_PH_TILE = 64 * C * 2;         // one offset of a phase-form weight: (2 x 32) rows x 32 ci
 constexpr int W_ROW_TILE = C * C * 2;         // one tap of a row-form weight
-constexpr int STG_BYTES = E2_WARPS * 32 * 16 * 4;
 constexpr int MAX_J = 11;
 struct Layout {
   int w1_bytes, w2_bytes, s_off, t_off, stg_off, bias_off, bar_off, total;
 };
-static Layout layout(int J, bool ph1) {
+static Layout layout(int J, bool ph1, int prep) {
   Layout l;
+  const int S_STAGES = s_stages(prep), STG_BYTES = e2_warps(prep) * 32 * cw(prep) * 4;
   l.w1_bytes = ph1 ? (J + 1) * W_PH_TILE : J * W_ROW_TILE;
   l.w2_bytes = (J + 1) * W_PH_TILE;
   l.s_off = l.w1_bytes + l.w2_bytes;
@@ -90,6 +103,8 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
                   const float* __restrict__ bias1, Epilogue ep, int variant, px::Layout lay, int tiles_per_clip,
                   int total_tiles, int dbg /*timing experiments only (DC_PAIRX_DBG): results are wrong when != 0*/) {
   using namespace px;
+  constexpr int NG2 = ng2(PREP_WARPS), S_STAGES = s_stages(PREP_WARPS), CW2 = cw(PREP_WARPS);
+  static_assert(threads<PREP_WARPS>() <= 1024 && 128 + NG2 * 64 <= 512, "thread / TMEM budget");
   constexpr uint32_t IDESC64 = ptx::make_idesc_bf16(128, 64), IDESC32 = ptx::make_idesc_bf16(128, 32);
   const int MO = TR - (J - 1), p1 = dil * (J - 1) / 2, p2 = (J - 1) / 2;
   const int rs = TR + (J - 1) * dil;        // rows of x one tile needs
@@ -140,7 +155,7 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc<512>(tmem_slot);   // D1[2] x 64 + D2[4] x 64 = 384 columns
+    ptx::tmem_alloc<512>(tmem_slot);   // D1[2] x 64 + D2[NG2] x 64 <= 512 columns
   }
   if (threadIdx.x < 64) sb1[threadIdx.x] = bias1[threadIdx.x & 31];   // conv1's bias for both rows of a super-row
   ptx::tc_fence_before();
@@ -368,7 +383,7 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     const int group = e2w / G2W;
     // warp id as epilogue_tile expects: (wg & 3) must be the hardware warp's TMEM lane quarter
     const int wg = 2 + ((warp - 2) & 3);
-    float* stg = reinterpret_cast<float*>(smem + lay.stg_off) + e2w * (32 * 16);
+    float* stg = reinterpret_cast<float*>(smem + lay.stg_off) + e2w * (32 * CW2);
     Epilogue epf = ep;        // prefetch only what prep has not just pulled into L2 (the mean's two other branches)
     if (PREP_WARPS > 0) epf.res = nullptr;
     const int T2 = T >> 1;
@@ -381,8 +396,8 @@ conv_pairx_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       ptx::mbar_wait_sleepy(&d2full[group], (uint32_t)(i / NG2) & 1u);
       ptx::tc_fence_after();
       if (!(dbg & 8)) {
-        epilogue_tile<64, 16>(ep, variant, stg, tm_d2 + group * 64, clip, v0, 0, T2, wg, lane, vlim);
-        epilogue_tile<64, 16>(ep, variant, stg, tm_d2 + group * 64, clip, v0, 0, T2, wg + 4, lane, vlim);
+        epilogue_tile<64, CW2>(ep, variant, stg, tm_d2 + group * 64, clip, v0, 0, T2, wg, lane, vlim);
+        epilogue_tile<64, CW2>(ep, variant, stg, tm_d2 + group * 64, clip, v0, 0, T2, wg + 4, lane, vlim);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -405,7 +420,7 @@ bool conv_pairx_supported(const ConvGemmShape& s1, const ConvGemmShape& s2) {
   if (s1.shift0 != -s1.dil * (s1.J - 1) / 2 || s2.shift0 != -(s2.J - 1) / 2) return false;
   if (s1.B != s2.B || s1.T != s2.T || (s1.T & 1)) return false;
   if (px::TR + (s1.J - 1) * s1.dil > px::S_ROWS) return false;
-  return px::layout(s1.J, s1.dil == 1).total <= 232448;
+  return px::layout(s1.J, s1.dil == 1, 0).total <= 232448 && px::layout(s1.J, s1.dil == 1, 8).total <= 232448;
 }
 
 // W1: conv1 weight, phase form [64][(J+1)*32] when s1.dil == 1, else row form [32][J*32]; W2p: conv2 phase form;
@@ -418,7 +433,7 @@ static int launch_px(const float* X, const __nv_bfloat16* S, const __nv_bfloat16
   using namespace px;
   const int J = s1.J;
   const bool ph1 = s1.dil == 1;
-  const Layout lay = layout(J, ph1);
+  const Layout lay = layout(J, ph1, PREP);
   static std::atomic<unsigned> attr_dev_mask{0u};  // once per (function, device); atomic because host threads driving different devices meet here
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
