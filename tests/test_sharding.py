@@ -115,3 +115,22 @@ def test_partition_and_tiles_properties_hypothesis():
 
     shards()
     tiles()
+
+
+def test_rows_pitch_collapses_strided_views_for_dma():
+    """Host logic of dc_copy2d_async: a time tile / per-clip crop of a (B, C, T) or (B, T) tensor is `rows` runs of
+    `width` bytes at a constant pitch; views that do not collapse are refused rather than silently staged."""
+    import pytest
+    from distilcodec_nabeel_b200.sharding import _rows_pitch
+    m = torch.empty(4, 128, 1000)
+    assert _rows_pitch(m) == (512, 4000, 4000)
+    assert _rows_pitch(m[1:3, :, 10:200]) == (256, 760, 4000)          # mel[b0:b1, :, lo:hi]
+    c = torch.empty(5, 300, dtype=torch.int64)
+    assert _rows_pitch(c[2:4, 7:57]) == (2, 400, 2400)                 # codes[b0:b1, s:e]
+    assert _rows_pitch(c[1:2, 7:57]) == (1, 400, 400)
+    assert _rows_pitch(torch.empty(3, 50)[:, 5:9]) == (3, 16, 200)
+    assert _rows_pitch(m[:, ::2, :]) == (256, 4000, 8000)              # every other row still is one constant pitch
+    with pytest.raises(ValueError):
+        _rows_pitch(m[:, :100, :])                                     # two different leading pitches
+    with pytest.raises(ValueError):
+        _rows_pitch(m.transpose(1, 2))                                 # last dimension not contiguous
