@@ -158,6 +158,7 @@ struct dc_handle_s {
   // C = 32 stage, fused ResBlock steps: 0 = conv_ws_pair (conv_ws.cu); 1 = conv_pair.cu on the fp32 stream (no bf16 side
   // buffer); 2 = conv_pair.cu with the bf16 side buffer as input (phase-form MMAs, data flow of conv_ws_pair)
   int pairx = 2;
+  int tsw_cluster = 2;  // wide decoder convs (conv_tsw) as CTA pairs that TMA-multicast their weight tiles (1 = off)
   int epi_prefetch = 1;
 
   // encoder
@@ -378,7 +379,7 @@ static int pack_block(dc_handle_s* h, const std::string& p, Block* blk, cudaStre
 
 // ---- layer runners --------------------------------------------------------------------------------------
 static int run_dense(const dc_handle_s* h, const Dense& d, const void* A, int B, int T, Epilogue ep, cudaStream_t st) {
-  ConvGemmShape s{B, T, d.C, d.J, d.shift0, d.dil, d.N, d.alg_scale, d.phase_cols, d.zero_taps};
+  ConvGemmShape s{B, T, d.C, d.J, d.shift0, d.dil, d.N, d.alg_scale, d.phase_cols, d.zero_taps, h->tsw_cluster};
   if (!ep.bias) ep.bias = d.bias;
   ep.ldo = d.N;
   ep.prefetch = h->epi_prefetch;
@@ -851,6 +852,9 @@ int dc_set_option(dc_handle h, const char* key, double value) {
     h->vq_x2_exact = value != 0.0;
   } else if (!strcmp(key, "fuse_pairs")) {
     h->fuse_pairs = value != 0.0;
+  } else if (!strcmp(key, "tsw_cluster")) {
+    DC_CHECK(value == 1.0 || value == 2.0, DC_ERR_ARG, "tsw_cluster must be 1 or 2");
+    h->tsw_cluster = (int)value;
   } else if (!strcmp(key, "pairx")) {
     DC_CHECK(value == 0.0 || value == 1.0 || value == 2.0, DC_ERR_ARG, "pairx must be 0, 1 or 2");
     h->pairx = (int)value;
@@ -1231,6 +1235,7 @@ int dc_op_conv_gemm(dc_handle h, const float* a_dev, const float* w_dev, const f
   e.out0_dt = DT_F32;
   e.ldo = N;
   ConvGemmShape s{B, T, C, J, shift0, dil, N};
+  s.cluster = h->tsw_cluster;
   int rc;
   if (h->mode == DC_MODE_BF16) {
     __nv_bfloat16 *ab = nullptr, *wb = nullptr;

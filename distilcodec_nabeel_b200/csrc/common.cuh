@@ -49,6 +49,7 @@ struct ConvGemmShape {
   // whole N tile lies inside one phase)
   int phase_cols = 0;
   uint32_t zero_taps = 0;
+  int cluster = 1;  // 2: kernels that support it run as CTA pairs sharing (TMA-multicasting) their weight tiles
 };
 
 // Runtime epilogue, applied per output element v = acc:

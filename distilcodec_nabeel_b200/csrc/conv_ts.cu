@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <string.h>
+
 #include "epilogue.cuh"
 
 namespace dc {
@@ -254,12 +256,25 @@ struct Cfg {
 };
 }  // namespace tsw
 
-template <int EG, int CW, int BST>
+// CL = 2: the kernel runs as thread-block clusters of two CTAs that work on ADJACENT row tiles of the same N block, i.e. on
+// the same weight tiles: each CTA loads one half (128 of the 256 weight rows) of every (tap, chunk) tile and TMA-multicasts
+// it into both CTAs' rings, so the L2 -> SM weight traffic per CTA halves (weights are ~94 % of this kernel's operand
+// traffic: 44 x 32 KB per tile against 4 x 23 KB of activations at k = 11, C = 256) and a ring of the same depth covers
+// twice the L2 round trip.  A weight slot is released to BOTH producers (multicast commit, empty barrier count 2).
+// A pair whose second row tile does not exist runs it as a ghost (TMA zero-fills, nothing is stored).
+template <int EG, int CW, int BST, int CL>
 __global__ void __launch_bounds__(64 + EG * 256, 1)
 conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvGemmShape s,
                 Epilogue ep, int variant, int tiles_per_clip, int m_tiles, int n_tiles) {
   using namespace tsw;
   using L = Cfg<EG, CW, BST>;
+  // work items: CL = 1: item = (m_blk, n_blk), N fastest; CL = 2: item = (pair of row tiles, n_blk), this CTA takes
+  // row tile 2 * pair + rank
+  const int rank = CL == 2 ? (int)ptx::cluster_ctarank() : 0;
+  const int worker = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_items = CL == 2 ? (m_tiles + 1) / 2 : m_tiles;
+  auto item_m_blk = [&](int item) { return CL == 2 ? 2 * (item / n_tiles) + rank : item / n_tiles; };
   constexpr int B_STAGES = BST, STG_OFF = L::STG_OFF, BAR_OFF = L::BAR_OFF;
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, BN);
   extern __shared__ uint8_t smem_raw[];
@@ -277,7 +292,7 @@ conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int kchunks = s.C / BK;
-  const int total_tiles = m_tiles * n_tiles;
+  const int total_tiles = m_items * n_tiles;
   const uint32_t a_bytes = (uint32_t)(((128 + (s.J - 1) * s.dil + 7) / 8 * 8) * BK * 2);
 
   if (warp == 0 && lane == 0) {
@@ -292,7 +307,7 @@ conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       for (int i = 0; i < B_STAGES; ++i) {
         ptx::mbar_init(&bfull[i], 1);
-        ptx::mbar_init(&bempty[i], 1);
+        ptx::mbar_init(&bempty[i], CL);   // released by the MMAs of every CTA the slot is multicast to
       }
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&tfull[i], 1);
@@ -305,6 +320,7 @@ conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) ptx::cluster_sync();   // the peer's barriers are initialised before anything is multicast to them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -313,8 +329,8 @@ conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (ptx::elect_one()) {
       int as = 0, bs = 0;
       uint32_t aphase = 0, bphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n0 = (tile % n_tiles) * BN;
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
+        const int m_blk = item_m_blk(tile), n0 = (tile % n_tiles) * BN;
         const int clip = m_blk / tiles_per_clip, t0 = (m_blk % tiles_per_clip) * 128;
         for (int kc = 0; kc < kchunks; ++kc) {
           ptx::mbar_wait(&aempty[as], aphase ^ 1);
@@ -324,7 +340,14 @@ conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int j = 0; j < s.J; ++j) {
             ptx::mbar_wait(&bempty[bs], bphase ^ 1);
             ptx::mbar_expect_tx(&bfull[bs], B_BYTES);
-            ptx::tma_load_2d(sB + bs * B_BYTES, &tmW, &bfull[bs], j * s.C + kc * BK, n0);
+            // the weight tile comes as two boxes of 128 rows: both from this CTA, or one from each CTA of the pair
+            if constexpr (CL == 2) {
+              ptx::tma_load_2d_multicast(sB + bs * B_BYTES + rank * (B_BYTES / 2), &tmW, &bfull[bs], j * s.C + kc * BK,
+                                         n0 + rank * (BN / 2), (uint16_t)3);
+            } else {
+              ptx::tma_load_2d(sB + bs * B_BYTES, &tmW, &bfull[bs], j * s.C + kc * BK, n0);
+              ptx::tma_load_2d(sB + bs * B_BYTES + B_BYTES / 2, &tmW, &bfull[bs], j * s.C + kc * BK, n0 + BN / 2);
+            }
             if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
           }
         }
@@ -336,7 +359,7 @@ conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int as = 0, bs = 0, it = 0;
       uint32_t aphase = 0, bphase = 0;
       const uint32_t tap_step = (uint32_t)(s.dil * BK * 2) >> 4;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers, ++it) {
         const int p = it & 1;
         TTRACE(0, it);
         ptx::mbar_wait(&tempty[p], ((it >> 1) & 1) ^ 1);
@@ -367,7 +390,8 @@ conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t acc = (kc | j) != 0 ? 1u : 0u;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) ptx::mma_bf16_ss(d0, da + 2 * k, db + 2 * k, IDESC, acc | (uint32_t)(k != 0));
-            ptx::mma_commit(&bempty[bs]);
+            if constexpr (CL == 2) ptx::mma_commit_multicast(&bempty[bs], (uint16_t)3);
+            else ptx::mma_commit(&bempty[bs]);
             if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
             da += tap_step;
           }
@@ -387,17 +411,18 @@ conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int group = (warp - 2) >> 3;
     const int wg = 2 + ((warp - 2) & 7);
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < total_tiles; tile += n_workers, ++it) {
       if (EG > 1 && (it & 1) != group) continue;
-      const int m_blk = tile / n_tiles, n0 = (tile % n_tiles) * BN;
+      const int m_blk = item_m_blk(tile), n0 = (tile % n_tiles) * BN;
       const int clip = m_blk / tiles_per_clip, t0 = (m_blk % tiles_per_clip) * 128;
+      const bool ghost = m_blk >= m_tiles;   // CL = 2, odd number of row tiles: the pair's second tile does not exist
       const int p = it & 1;
-      epilogue_prefetch(ep, clip, s.T, t0 + (wg & 3) * 32, n0 + ((wg - 2) >> 2) * (BN / 2), BN / 2, lane);
+      if (!ghost) epilogue_prefetch(ep, clip, s.T, t0 + (wg & 3) * 32, n0 + ((wg - 2) >> 2) * (BN / 2), BN / 2, lane);
       if (wg == 2 && lane == 0) TTRACE(5, it);
       ptx::mbar_wait_sleepy(&tfull[p], (it >> 1) & 1);
       if (wg == 2 && lane == 0) TTRACE(6, it);
       ptx::tc_fence_after();
-      epilogue_tile<BN, CW>(ep, variant, stg, tmem_base + p * BN, clip, t0, n0, s.T, wg, lane);
+      if (!ghost) epilogue_tile<BN, CW>(ep, variant, stg, tmem_base + p * BN, clip, t0, n0, s.T, wg, lane);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[p]);
@@ -407,6 +432,7 @@ conv_tsw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) ptx::cluster_sync();   // no CTA exits while its peer may still multicast into it
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
@@ -418,7 +444,7 @@ bool conv_tsw_supported(const ConvGemmShape& s) {
          128 + (s.J - 1) * s.dil <= tsw::A_ROWS;
 }
 
-template <int EG, int CW, int BST>
+template <int EG, int CW, int BST, int CL>
 static int launch_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
                       cudaStream_t st, int sm_count) {
   using namespace tsw;
@@ -427,7 +453,7 @@ static int launch_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
   if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
-    DC_CUDA(cudaFuncSetAttribute(conv_tsw_kernel<EG, CW, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
+    DC_CUDA(cudaFuncSetAttribute(conv_tsw_kernel<EG, CW, BST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
     attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
   }
   const int tiles_per_clip = (s.T + 127) / 128;
@@ -446,11 +472,13 @@ static int launch_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
     const uint64_t K = (uint64_t)s.J * s.C;
     const uint64_t dims[2] = {K, (uint64_t)s.N};
     const uint64_t strides[1] = {K * 2};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(BN / 2)};   // a weight tile = two boxes of 128 rows
     DC_TRY(make_tmap_bf16(&tmW, W, 2, dims, strides, box, 128));
   }
-  const long long total = m_tiles * n_tiles;
-  const int grid = (int)(total < sm_count ? total : sm_count);
+  // CL = 1: one CTA per (row tile, N block); CL = 2: one CTA PAIR per (two row tiles, N block)
+  const long long total = ((m_tiles + CL - 1) / CL) * n_tiles;
+  const long long workers = total < sm_count / CL ? total : sm_count / CL;
+  const int grid = (int)workers * CL;
   {
     const double rows = (double)s.B * s.T;
     const double macs = rows * s.N * s.J * s.C * s.alg_scale;
@@ -459,13 +487,27 @@ static int launch_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
     const double out_bytes = (e.out0 ? (e.out0_dt == DT_F32 ? 4.0 : 2.0) : 0.0) + (e.out1 ? 2.0 : 0.0) +
                              (e.res ? 4.0 : 0.0) + (e.add1 ? 8.0 : 0.0);
     ProfScope ps(PC_CONV_TS, 2.0 * macs, rows * s.C * 2.0 + (double)s.N * s.J * s.C * 2.0 + rows * s.N * out_bytes, st,
-                 "w<%d,%d,%d>|C%d N%d J%d d%d e%d", EG, CW, BST, s.C, s.N, s.J, s.dil, esig);
+                 CL == 2 ? "w<%d,%d,%d>x2|C%d N%d J%d d%d e%d" : "w<%d,%d,%d>|C%d N%d J%d d%d e%d", EG, CW, BST, s.C, s.N,
+                 s.J, s.dil, esig);
     Epilogue eg = e;
     // L2-prefetching the residual tile while the MMAs run pays only where the layer is HBM-latency-bound (A/B on one
     // box: k = 3 at C = 256 -6 % / -11 %; k = 7 +9 %; the tensor-bound k = 11 layers lose ~3 %)
     eg.prefetch = (s.J * s.C <= 768) ? e.prefetch : 0;
-    conv_tsw_kernel<EG, CW, BST><<<grid, 64 + EG * 256, TOTAL, st>>>(tmA, tmW, s, eg, epilogue_variant(e), tiles_per_clip,
-                                                            (int)m_tiles, n_tiles);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(64 + EG * 256);
+    cfg.dynamicSmemBytes = TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    DC_CUDA(cudaLaunchKernelEx(&cfg, conv_tsw_kernel<EG, CW, BST, CL>, tmA, tmW, s, eg, epilogue_variant(e), tiles_per_clip,
+                               (int)m_tiles, n_tiles));
   }
   ++g_launches_ts;
   DC_CUDA(cudaGetLastError());
@@ -475,11 +517,14 @@ static int launch_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
 int launch_conv_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
                     cudaStream_t st, int sm_count) {
   DC_CHECK(conv_tsw_supported(s), DC_ERR_SHAPE, "conv_tsw: unsupported shape");
+  // CTA pairs (weight multicast) need at least one full pair of row tiles and an even share of the SMs
+  const bool pair = s.cluster == 2 && (long long)s.B * ((s.T + 127) / 128) >= 2 && sm_count >= 2;
   if (e.res || (e.out0 && e.out1)) {
-    if (s.J * s.C <= 1792 && s.N == 256) return launch_tsw<2, 32, 3>(A, W, s, e, st, sm_count);
-    return launch_tsw<2, 16, 4>(A, W, s, e, st, sm_count);
+    if (s.J * s.C <= 1792 && s.N == 256)
+      return pair ? launch_tsw<2, 32, 3, 2>(A, W, s, e, st, sm_count) : launch_tsw<2, 32, 3, 1>(A, W, s, e, st, sm_count);
+    return pair ? launch_tsw<2, 16, 4, 2>(A, W, s, e, st, sm_count) : launch_tsw<2, 16, 4, 1>(A, W, s, e, st, sm_count);
   }
-  return launch_tsw<1, 32, 4>(A, W, s, e, st, sm_count);
+  return pair ? launch_tsw<1, 32, 4, 2>(A, W, s, e, st, sm_count) : launch_tsw<1, 32, 4, 1>(A, W, s, e, st, sm_count);
 }
 
 bool conv_ts_supported(const ConvGemmShape& s) {

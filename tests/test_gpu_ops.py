@@ -118,3 +118,41 @@ def test_layout_helpers_round_trip():
     nlc = eng.ncl_to_nlc(x)
     assert torch.equal(nlc, x.transpose(1, 2).contiguous())
     assert eng.ncl_to_nlc(nlc.transpose(1, 2)).data_ptr() == nlc.data_ptr()   # zero-copy for NLC-backed views
+
+
+# (B, T, C, N, k, dil, act, with_res): wide convs (conv_tsw) with odd / even / single row-tile counts
+PAIR_CASES = [
+    (1, 300, 256, 256, 7, 1, 0, True),      # 3 row tiles: the last pair runs a ghost tile
+    (3, 130, 512, 512, 3, 5, 2, False),     # 6 row tiles, two N blocks
+    (2, 300, 256, 256, 11, 5, 0, True),     # largest halo
+    (1, 641, 512, 1024, 3, 1, 0, False),    # 6 row tiles (ragged last), four N blocks
+    (5, 128, 256, 512, 7, 3, 2, False),     # 5 single-tile clips: pairs straddle clips
+    (1, 100, 256, 256, 3, 1, 0, False),     # one row tile: falls back to single CTAs
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=lambda c: "B%dT%dC%dN%dk%dd%da%dr%d" % tuple(int(v) for v in c))
+def test_wide_conv_cta_pairs_with_weight_multicast(case):
+    """conv_tsw as clusters of two CTAs that TMA-multicast the weight tiles (option "tsw_cluster" = 2) against the same
+    kernel as single CTAs and against torch: the MMA sequence per tile is unchanged, so the results are bit-identical."""
+    B, T, C, N, k, dil, act, with_res = case
+    eng = engine("W1", "bf16", 1024)
+    a = _rand(B, T, C, seed=11)
+    w = _rand(N, C, k, seed=12, scale=(C * k) ** -0.5)
+    bias = _rand(N, seed=13, scale=0.1)
+    res = _rand(B, T, N, seed=14) if with_res else None
+    pad = dil * (k - 1) // 2
+    ref = _conv_ref(a, w, bias, dil, pad, act, res)
+    w_pack = w.permute(0, 2, 1).reshape(N, k * C).contiguous()
+    dev = eng.device
+    args = (a.to(dev), w_pack.to(dev), bias.to(dev), None if res is None else res.to(dev), -pad, dil, act)
+    outs = {}
+    try:
+        for cl in (1, 2):
+            eng.set_option("tsw_cluster", cl)
+            outs[cl] = eng.op_conv_gemm(*args)
+            torch.cuda.synchronize()
+    finally:
+        eng.set_option("tsw_cluster", 2)
+    assert rel_err(outs[2], ref) < TOL["bf16"]
+    assert torch.equal(outs[1], outs[2])
