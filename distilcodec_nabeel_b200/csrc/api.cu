@@ -158,7 +158,9 @@ struct dc_handle_s {
   // C = 32 stage, fused ResBlock steps: 0 = conv_ws_pair (conv_ws.cu); 1 = conv_pair.cu on the fp32 stream (no bf16 side
   // buffer); 2 = conv_pair.cu with the bf16 side buffer as input (phase-form MMAs, data flow of conv_ws_pair)
   int pairx = 2;
-  int tsw_cluster = 2;  // wide decoder convs (conv_tsw) as CTA pairs that TMA-multicast their weight tiles (1 = off)
+  // 2: the tensor-bound kernels whose CTAs stream the same weight / codebook tiles (conv_tsw, gemm_tc with N tiles of 256,
+  // vq_score) run as CTA pairs (thread-block clusters) that TMA-multicast those tiles to each other; 1: single CTAs
+  int tsw_cluster = 2;
   int epi_prefetch = 1;
 
   // encoder
@@ -547,7 +549,8 @@ static int stage_quantizer(const dc_handle_s* h, const float* enc, int B, int T,
     DC_TRY(run_dense(h, h->proj_in, zop, B, T, e, st));
   }
   DC_TRY(launch_vq_search(x_pjt_in, ad, nullptr, (int64_t)rows, CD, h->codebook, h->codebook_bf16, h->c2, h->c2max,
-                          h->K, codes, vq_ws, vq_bytes, h->vq_window, h->vq_tc, h->vq_x2_exact, st, h->sm_count, nullptr));
+                          h->K, codes, vq_ws, vq_bytes, h->vq_window, h->vq_tc, h->vq_x2_exact, st, h->sm_count, nullptr,
+                          h->tsw_cluster));
   if (codes_only) return DC_OK;
   // batched_embedding (vector_quantize_pytorch.py:243-247,506): quantized_fup = codebook rows
   const void* fop;
@@ -852,8 +855,8 @@ int dc_set_option(dc_handle h, const char* key, double value) {
     h->vq_x2_exact = value != 0.0;
   } else if (!strcmp(key, "fuse_pairs")) {
     h->fuse_pairs = value != 0.0;
-  } else if (!strcmp(key, "tsw_cluster")) {
-    DC_CHECK(value == 1.0 || value == 2.0, DC_ERR_ARG, "tsw_cluster must be 1 or 2");
+  } else if (!strcmp(key, "cta_pairs") || !strcmp(key, "tsw_cluster")) {
+    DC_CHECK(value == 1.0 || value == 2.0, DC_ERR_ARG, "cta_pairs must be 1 or 2");
     h->tsw_cluster = (int)value;
   } else if (!strcmp(key, "pairx")) {
     DC_CHECK(value == 0.0 || value == 1.0 || value == 2.0, DC_ERR_ARG, "pairx must be 0, 1 or 2");
@@ -1187,7 +1190,7 @@ int dc_vq_search(dc_handle h, const void* x_dev, int x_is_bf16, const float* x2_
   return launch_vq_search(x_dev, x_is_bf16 ? DT_BF16 : DT_F32, x2_dev, N, h->CD, h->codebook, h->codebook_bf16, h->c2,
                           h->c2max, h->K, codes_dev, ws_dev ? ws : nullptr, ws_bytes > lost ? ws_bytes - lost : 0,
                           h->vq_window, h->vq_tc, h->vq_x2_exact, reinterpret_cast<cudaStream_t>(stream), h->sm_count,
-                          stats_host);
+                          stats_host, h->tsw_cluster);
 }
 
 int dc_mel_forward(dc_handle h, const float* audio_dev, int B, int Ls, float* mel_ncl_dev, void* stream) {

@@ -191,7 +191,7 @@ size_t vq_workspace_bytes(int64_t nrows, int D, bool x_is_bf16);
 int launch_vq_search(const void* x, int x_dt, const float* x2_opt, int64_t nrows, int D, const float* codebook_f32,
                      const __nv_bfloat16* codebook_bf16, const float* c2, const float* c2max_dev, int K,
                      int64_t* codes, void* ws, size_t ws_bytes, float window_factor, bool use_tc, bool x2_exact,
-                     cudaStream_t st, int sm_count, int* stats_host_opt);
+                     cudaStream_t st, int sm_count, int* stats_host_opt, int cta_pairs = 1);
 int launch_vq_resid_max(const float* cb, int64_t rows, int D, float* out /*1 float*/, cudaStream_t st);
 int launch_row_sqnorm_torch_order(const float* in, float* out, int64_t rows, int D, cudaStream_t st);
 uint64_t vq_launch_count();

@@ -58,12 +58,19 @@ struct Cfg {
 constexpr int MAX_A_ROWS = 320;
 }  // namespace ts
 
-template <int BOXR, int AST, int BST>
+// CL = 2: CTA pairs on adjacent 256-row tiles TMA-multicast the (tap, chunk) weight tiles to each other (each loads 64 of
+// the 128 weight rows), see conv_tsw_kernel below; item i of a pair = tiles 2i and 2i + 1, a missing second tile is a ghost.
+template <int BOXR, int AST, int BST, int CL>
 __global__ void __launch_bounds__(ts::THREADS, 1)
 conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvGemmShape s,
                Epilogue ep, int variant, int tiles_per_clip, int total_tiles) {
   using namespace ts;
   using L = Cfg<BOXR, AST, BST>;
+  const int rank = CL == 2 ? (int)ptx::cluster_ctarank() : 0;
+  const int worker = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_items = CL == 2 ? (total_tiles + 1) / 2 : total_tiles;
+  auto item_tile = [&](int item) { return CL == 2 ? 2 * item + rank : item; };
   constexpr int BOX_ROWS = BOXR, A_BYTES = L::A_BYTES, B_STAGES = BST, A_STAGES = AST;
   constexpr int A_OFF = L::A_OFF, B_OFF = L::B_OFF, STG_OFF = L::STG_OFF, BAR_OFF = L::BAR_OFF;
   // Operand roles are swapped: the WEIGHT tile (128 output channels x 64) is the MMA's A operand (M = 128) and the
@@ -98,7 +105,7 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int i = 0; i < B_STAGES; ++i) {
         ptx::mbar_init(&bfull[i], 1);
-        ptx::mbar_init(&bempty[i], 1);
+        ptx::mbar_init(&bempty[i], CL);
       }
       for (int i = 0; i < 2; ++i) {
         ptx::mbar_init(&tfull[i], 1);
@@ -111,6 +118,7 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -123,10 +131,10 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr int AHEAD = A_STAGES >= 3 ? 1 : 0;
       int bs = 0, as = 0;
       uint32_t bphase = 0, aphase = 0;
-      const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int my_tiles = worker < n_items ? (n_items - worker + n_workers - 1) / n_workers : 0;
       const int n_chunks = my_tiles * KCH;
       auto load_a = [&](int c) {  // chunk c of this CTA's sequence = (tile c / KCH, channel chunk c % KCH)
-        const int tile = blockIdx.x + (c / KCH) * gridDim.x, kc = c % KCH;
+        const int tile = item_tile(worker + (c / KCH) * n_workers), kc = c % KCH;
         const int clip = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * 256;
         ptx::mbar_wait(&aempty[as], aphase ^ 1);
         ptx::mbar_expect_tx(&afull[as], A_BYTES);
@@ -141,7 +149,11 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < s.J; ++j) {
           ptx::mbar_wait(&bempty[bs], bphase ^ 1);
           ptx::mbar_expect_tx(&bfull[bs], B_BYTES);
-          ptx::tma_load_2d(sB + bs * B_BYTES, &tmW, &bfull[bs], j * C + kc * BK, 0);
+          if constexpr (CL == 2)
+            ptx::tma_load_2d_multicast(sB + bs * B_BYTES + rank * (B_BYTES / 2), &tmW, &bfull[bs], j * C + kc * BK,
+                                       rank * (N / 2), (uint16_t)3);
+          else
+            ptx::tma_load_2d(sB + bs * B_BYTES, &tmW, &bfull[bs], j * C + kc * BK, 0);
           if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
         }
       }
@@ -152,7 +164,7 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int bs = 0, as = 0, it = 0;
       uint32_t bphase = 0, aphase = 0;
       const uint32_t tap_step = (uint32_t)(s.dil * BK * 2) >> 4;   // descriptor start-address units (16 B) per tap
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int item = worker; item < n_items; item += n_workers, ++it) {
         const int p = it & 1;
         TTRACE(0, it);
         ptx::mbar_wait(&tempty[p], ((it >> 1) & 1) ^ 1);
@@ -184,7 +196,8 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)  // D[channel, row] += W[channel, k] * A[row + j*dil, k]
               ptx::mma_bf16_ss(d0, db + 2 * k, da + 2 * k, IDESC, acc | (uint32_t)(k != 0));
-            ptx::mma_commit(&bempty[bs]);
+            if constexpr (CL == 2) ptx::mma_commit_multicast(&bempty[bs], (uint16_t)3);
+            else ptx::mma_commit(&bempty[bs]);
             if (++bs == B_STAGES) { bs = 0; bphase ^= 1; }
             da += tap_step;  // tap j + 1 = the same rows, dil rows further down
           }
@@ -204,17 +217,21 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // epilogue warp index whose low 2 bits equal the hardware warp's TMEM lane quarter (warp % 4)
     const int warp16 = (((warp - 2) >> 2) << 2) | (warp & 3);
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int item = worker; item < n_items; item += n_workers, ++it) {
+      const int tile = item_tile(item);
+      const bool ghost = tile >= total_tiles;
       const int clip = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * 256;
       const int p = it & 1;
       // this warp's region: 32 channels (one 128-byte line per row) x 64 rows
-      epilogue_prefetch(ep, clip, s.T, t0 + (warp16 >> 2) * 64, (warp16 & 3) * 32, 32, lane);
-      epilogue_prefetch(ep, clip, s.T, t0 + (warp16 >> 2) * 64 + 32, (warp16 & 3) * 32, 32, lane);
+      if (!ghost) {
+        epilogue_prefetch(ep, clip, s.T, t0 + (warp16 >> 2) * 64, (warp16 & 3) * 32, 32, lane);
+        epilogue_prefetch(ep, clip, s.T, t0 + (warp16 >> 2) * 64 + 32, (warp16 & 3) * 32, 32, lane);
+      }
       if (warp16 == 0 && lane == 0) TTRACE(5, it);
       ptx::mbar_wait_sleepy(&tfull[p], (it >> 1) & 1);
       if (warp16 == 0 && lane == 0) TTRACE(6, it);
       ptx::tc_fence_after();
-      epilogue_tile_transposed(ep, variant, stg, tmem_base + p * 256, clip, t0, s.T, warp16, lane);
+      if (!ghost) epilogue_tile_transposed(ep, variant, stg, tmem_base + p * 256, clip, t0, s.T, warp16, lane);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[p]);
@@ -224,6 +241,7 @@ conv_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) ptx::cluster_sync();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
@@ -531,7 +549,7 @@ bool conv_ts_supported(const ConvGemmShape& s) {
   return s.C == ts::C && s.N == ts::N && 256 + (s.J - 1) * s.dil <= ts::MAX_A_ROWS && s.J >= 1;
 }
 
-template <int BOXR, int AST, int BST>
+template <int BOXR, int AST, int BST, int CL>
 static int launch_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
                      cudaStream_t st, int sm_count) {
   using namespace ts;
@@ -541,7 +559,7 @@ static int launch_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvG
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
   if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
-    DC_CUDA(cudaFuncSetAttribute(conv_ts_kernel<BOXR, AST, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
+    DC_CUDA(cudaFuncSetAttribute(conv_ts_kernel<BOXR, AST, BST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
     attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
   }
   const int tiles_per_clip = (s.T + 255) / 256;
@@ -558,10 +576,11 @@ static int launch_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvG
     const uint64_t K = (uint64_t)s.J * C;
     const uint64_t dims[2] = {K, (uint64_t)N};
     const uint64_t strides[1] = {K * 2};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)N};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(N / CL)};   // pairs: each CTA loads half the weight rows
     DC_TRY(make_tmap_bf16(&tmW, W, 2, dims, strides, box, 128));
   }
-  const int grid = (int)(total < sm_count ? total : sm_count);
+  const long long items = (total + CL - 1) / CL;
+  const int grid = (int)(items < sm_count / CL ? items : sm_count / CL) * CL;
   {
     const double rows = (double)s.B * s.T;
     const double macs = rows * N * s.J * C * s.alg_scale;
@@ -571,7 +590,21 @@ static int launch_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvG
                              (e.res ? 4.0 : 0.0) + (e.add1 ? 8.0 : 0.0);
     ProfScope ps(PC_CONV_TS, 2.0 * macs, rows * C * 2.0 + (double)N * s.J * C * 2.0 + rows * N * out_bytes, st,
                  AST == 2 ? "|C%d N%d J%d d%d e%d" : "<a3>|C%d N%d J%d d%d e%d", C, N, s.J, s.dil, esig);
-    conv_ts_kernel<BOXR, AST, BST><<<grid, THREADS, TOTAL, st>>>(tmA, tmW, s, e, epilogue_variant(e), tiles_per_clip, (int)total);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    DC_CUDA(cudaLaunchKernelEx(&cfg, conv_ts_kernel<BOXR, AST, BST, CL>, tmA, tmW, s, e, epilogue_variant(e), tiles_per_clip,
+                               (int)total));
   }
   ++g_launches_ts;
   DC_CUDA(cudaGetLastError());
@@ -581,10 +614,12 @@ static int launch_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvG
 int launch_conv_ts(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
                    cudaStream_t st, int sm_count) {
   DC_CHECK(conv_ts_supported(s), DC_ERR_SHAPE, "conv_ts: unsupported shape C=%d N=%d J=%d dil=%d", s.C, s.N, s.J, s.dil);
+  const bool pair = s.cluster == 2 && (long long)s.B * ((s.T + 255) / 256) >= 2 && sm_count >= 2;
 #ifndef DC_TS_NO_A3
-  if (s.J <= 3 && (s.J - 1) * s.dil <= 16) return launch_ts<136, 3, 3>(A, W, s, e, st, sm_count);
+  if (s.J <= 3 && (s.J - 1) * s.dil <= 16)
+    return pair ? launch_ts<136, 3, 3, 2>(A, W, s, e, st, sm_count) : launch_ts<136, 3, 3, 1>(A, W, s, e, st, sm_count);
 #endif
-  return launch_ts<160, 2, 5>(A, W, s, e, st, sm_count);
+  return pair ? launch_ts<160, 2, 5, 2>(A, W, s, e, st, sm_count) : launch_ts<160, 2, 5, 1>(A, W, s, e, st, sm_count);
 }
 
 }  // namespace dc

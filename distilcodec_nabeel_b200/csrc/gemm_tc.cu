@@ -14,6 +14,8 @@
 // Tiles are ordered n-fastest so the CTAs running at any moment share a few A row-blocks (read from HBM once) and
 // all of W (<= 27 MB, L2 resident).
 #include "common.cuh"
+
+#include <string.h>
 #include "ptx.cuh"
 
 #include <mutex>
@@ -94,11 +96,19 @@ struct GemmTcSmem {
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-template <int BN, int BK, int STAGES, int EG, int ACC>
+// CL = 2 (BN = 256 only): thread-block clusters of two CTAs work on adjacent row tiles of the same N block and each
+// TMA-multicasts one half (128 rows) of every weight tile into both CTAs' rings (see conv_tsw_kernel, conv_ts.cu).
+template <int BN, int BK, int STAGES, int EG, int ACC, int CL>
 __global__ void __launch_bounds__(64 + EG * 256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvGemmShape s,
                Epilogue ep, int variant, int tiles_per_clip, int m_tiles, int n_tiles) {
   using L = GemmTcSmem<BN, BK, STAGES, EG>;
+  static_assert(CL == 1 || BN == 256, "weight multicast splits a 256-row tile into two 128-row boxes");
+  const int rank = CL == 2 ? (int)ptx::cluster_ctarank() : 0;
+  const int worker = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_items = CL == 2 ? (m_tiles + 1) / 2 : m_tiles;
+  auto item_m_blk = [&](int item) { return CL == 2 ? 2 * (item / n_tiles) + rank : item / n_tiles; };
   constexpr int SW = BK * 2;  // swizzle span = one K-row of the tile in bytes (128 or 64)
   constexpr int TMEM_COLS = ACC * BN;
   static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
@@ -125,7 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) {
         ptx::mbar_init(&full[i], 1);
-        ptx::mbar_init(&empty[i], 1);
+        ptx::mbar_init(&empty[i], CL);   // a stage is released by the MMAs of every CTA its weight tile is multicast to
       }
       for (int i = 0; i < ACC; ++i) {
         ptx::mbar_init(&tfull[i], 1);
@@ -138,10 +148,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) ptx::cluster_sync();   // the peer's barriers exist before anything is multicast to them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = m_tiles * n_tiles;
+  const int total_tiles = m_items * n_tiles;
   const int kchunks = s.C / BK;
 
   if (warp == 0) {
@@ -149,8 +160,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (ptx::elect_one()) {  // one lane, known to the compiler: operands go to uniform registers
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
+        const int m_blk = item_m_blk(tile), n_blk = tile % n_tiles;
         const int clip = m_blk / tiles_per_clip, t0 = (m_blk % tiles_per_clip) * 128, n0 = n_blk * BN;
         const uint32_t skip = tile_zero_taps(s, n0, BN);
         for (int j = 0; j < s.J; ++j) {
@@ -160,7 +171,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_wait(&empty[stage], phase ^ 1);
             ptx::mbar_expect_tx(&full[stage], L::A_BYTES + L::B_BYTES);
             ptx::tma_load_3d(sA + stage * L::A_BYTES, &tmA, &full[stage], kc * BK, trow, clip);
-            ptx::tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full[stage], j * s.C + kc * BK, n0);
+            if constexpr (CL == 2)   // this CTA's half of the weight tile, into both CTAs
+              ptx::tma_load_2d_multicast(sB + stage * L::B_BYTES + rank * (L::B_BYTES / 2), &tmB, &full[stage],
+                                         j * s.C + kc * BK, n0 + rank * (BN / 2), (uint16_t)3);
+            else
+              ptx::tma_load_2d(sB + stage * L::B_BYTES, &tmB, &full[stage], j * s.C + kc * BK, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -172,7 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers, ++it) {
         const int as = it % ACC;
         const uint32_t aphase = (it / ACC) & 1;
         ptx::mbar_wait(&tempty[as], aphase ^ 1);
@@ -191,7 +206,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t db = ptx::make_smem_desc<SW>(b_addr + k * 32);
             ptx::mma_bf16_ss(d_tmem, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
           }
-          ptx::mma_commit(&empty[stage]);  // frees the smem slot when these MMAs have read it
+          if constexpr (CL == 2) ptx::mma_commit_multicast(&empty[stage], (uint16_t)3);
+          else ptx::mma_commit(&empty[stage]);  // frees the smem slot when these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         ptx::mma_commit(&tfull[as]);  // accumulator complete
@@ -203,16 +219,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int group = (warp - 2) >> 3;
     const int wg = 2 + ((warp - 2) & 7);  // warp id within its group (2..9), keeps warp % 4 = TMEM lane quarter
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < total_tiles; tile += n_workers, ++it) {
       if (EG > 1 && it % EG != group) continue;
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int m_blk = item_m_blk(tile), n_blk = tile % n_tiles;
       const int clip = m_blk / tiles_per_clip, t0 = (m_blk % tiles_per_clip) * 128, n0 = n_blk * BN;
+      const bool ghost = m_blk >= m_tiles;   // CL = 2, odd number of row tiles: computed on zero rows, never stored
       const int as = it % ACC;
       const uint32_t aphase = (it / ACC) & 1;
-      epilogue_prefetch(ep, clip, s.T, t0 + (wg & 3) * 32, n0 + ((wg - 2) >> 2) * (BN / 2), BN / 2, lane);
+      if (!ghost) epilogue_prefetch(ep, clip, s.T, t0 + (wg & 3) * 32, n0 + ((wg - 2) >> 2) * (BN / 2), BN / 2, lane);
       ptx::mbar_wait_sleepy(&tfull[as], aphase);
       ptx::tc_fence_after();
-      epilogue_tile<BN, L::CW>(ep, variant, stg, tmem_base + as * BN, clip, t0, n0, s.T, wg, lane);
+      if (!ghost) epilogue_tile<BN, L::CW>(ep, variant, stg, tmem_base + as * BN, clip, t0, n0, s.T, wg, lane);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[as]);
@@ -221,6 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) ptx::cluster_sync();   // no CTA exits while its peer may still multicast into it
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -228,9 +246,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------- launcher
-template <int BN, int BK, int STAGES, int EG = 1, int ACC = 2>
-static int launch_cfg(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
-                      cudaStream_t st, int sm_count) {
+template <int BN, int BK, int STAGES, int EG, int ACC, int CL>
+static int launch_cfg_cl(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
+                         cudaStream_t st, int sm_count) {
   using L = GemmTcSmem<BN, BK, STAGES, EG>;
   static_assert(ACC * BN <= 512, "TMEM columns");
 
@@ -238,7 +256,7 @@ static int launch_cfg(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
   if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
-    DC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, STAGES, EG, ACC>,
+    DC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, BK, STAGES, EG, ACC, CL>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
   }
@@ -258,11 +276,12 @@ static int launch_cfg(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
     const uint64_t K = (uint64_t)s.J * s.C;
     const uint64_t dims[2] = {K, (uint64_t)s.N};
     const uint64_t strides[1] = {K * 2};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(BN / CL)};   // CL = 2: each CTA of a pair loads half the rows
     DC_TRY(make_tmap_bf16(&tmB, W, 2, dims, strides, box, BK * 2));
   }
-  const long long total = m_tiles * n_tiles;
-  const int grid = (int)(total < sm_count ? total : sm_count);
+  const long long total = ((m_tiles + CL - 1) / CL) * n_tiles;
+  const long long workers = total < sm_count / CL ? total : sm_count / CL;
+  const int grid = (int)workers * CL;
   {
     const double rows = (double)s.B * s.T;
     const double macs = rows * s.N * s.J * s.C * s.alg_scale;
@@ -273,16 +292,40 @@ static int launch_cfg(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
     const double out_bytes = (e.out0 ? (e.out0_dt == DT_F32 ? 4.0 : 2.0) : 0.0) + (e.out1 ? 2.0 : 0.0) +
                              (e.res ? 4.0 : 0.0) + (e.add1 ? 8.0 : 0.0);
     ProfScope ps(PC_GEMM_TC, 2.0 * macs, rows * s.C * 2.0 + (double)s.N * s.J * s.C * 2.0 + rows * s.N * out_bytes, st,
-                 "<%d,%d,%d,%d,%d>|C%d N%d J%d d%d e%d", BN, BK, STAGES, EG, ACC, s.C, s.N, s.J, s.dil, esig);
+                 CL == 2 ? "<%d,%d,%d,%d,%d>x2|C%d N%d J%d d%d e%d" : "<%d,%d,%d,%d,%d>|C%d N%d J%d d%d e%d", BN, BK,
+                 STAGES, EG, ACC, s.C, s.N, s.J, s.dil, esig);
     Epilogue eg = e;
     eg.prefetch = 0;  // A/B on one B200: the L2 prefetch helps the HBM-bound narrow kernels (conv_ws/_pair/_ts,
                       // -5 %) but costs the tensor-bound wide ones 3 % (extra L2 traffic next to 17 TB/s of operands)
-    gemm_tc_kernel<BN, BK, STAGES, EG, ACC><<<grid, L::THREADS, L::TOTAL, st>>>(
-        tmA, tmB, s, eg, epilogue_variant(e), tiles_per_clip, (int)m_tiles, n_tiles);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(L::THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    DC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, BK, STAGES, EG, ACC, CL>, tmA, tmB, s, eg, epilogue_variant(e),
+                               tiles_per_clip, (int)m_tiles, n_tiles));
   }
   ++g_launches_tc;
   DC_CUDA(cudaGetLastError());
   return DC_OK;
+}
+
+template <int BN, int BK, int STAGES, int EG = 1, int ACC = 2>
+static int launch_cfg(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
+                      cudaStream_t st, int sm_count) {
+  if constexpr (BN == 256) {   // CTA pairs need one full pair of row tiles
+    if (s.cluster == 2 && (long long)s.B * ((s.T + 127) / 128) >= 2 && sm_count >= 2)
+      return launch_cfg_cl<BN, BK, STAGES, EG, ACC, 2>(A, W, s, e, st, sm_count);
+  }
+  return launch_cfg_cl<BN, BK, STAGES, EG, ACC, 1>(A, W, s, e, st, sm_count);
 }
 
 int launch_gemm_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s_in, const Epilogue& e,

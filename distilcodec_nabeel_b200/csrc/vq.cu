@@ -18,6 +18,8 @@
 //                            smallest distance wins, lowest index on ties.  Rows whose list overflowed go to pass 3.
 // Pass 3  vq_exhaustive_*    exact scan of the whole codebook for overflowed rows (degenerate inputs only).
 #include "common.cuh"
+
+#include <string.h>
 #include "ptx.cuh"
 
 #include <math.h>
@@ -270,6 +272,10 @@ __device__ __noinline__ void vq_append(int2* list, int& cnt, float thr, int idx,
   list[cnt++] = make_int2(idx, __float_as_int(s));
 }
 
+// CL = 2: thread-block clusters of two CTAs score adjacent 256-row blocks against the SAME codebook tiles; each CTA loads
+// one half (128 codes) of every codebook tile and TMA-multicasts it into both CTAs' rings, so the codebook traffic from L2
+// per CTA halves (operand traffic 64 -> 48 KB per stage).  A stage is released to both producers (multicast commit).
+template <int CL>
 __global__ void __launch_bounds__(VQ_THREADS, 1)
 vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmC,
                 const float* __restrict__ c2, const float* __restrict__ win, float* __restrict__ best_out,
@@ -289,6 +295,12 @@ vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  // work items: (256-row block, codebook split); with CL = 2 an item is a PAIR of row blocks and this CTA takes block
+  // 2 * (item / NS) + rank (a block past the last row is a ghost: zero rows, nothing recorded)
+  const int rank = CL == 2 ? (int)ptx::cluster_ctarank() : 0;
+  const int worker = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto item_mblk = [&](int item) { return CL == 2 ? 2 * (item / NS) + rank : item / NS; };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmX);
@@ -298,7 +310,7 @@ vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (lane == 0) {
       for (int i = 0; i < VQ_STAGES; ++i) {
         ptx::mbar_init(&full[i], 1);
-        ptx::mbar_init(&empty[i], 1);
+        ptx::mbar_init(&empty[i], CL);
       }
       ptx::mbar_init(tfull, 1);
       ptx::mbar_init(tempty, 8);
@@ -309,6 +321,7 @@ vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) ptx::cluster_sync();   // the peer's barriers exist before anything is multicast to them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -317,8 +330,8 @@ vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (ptx::elect_one()) {  // one lane, known to the compiler: operands go to uniform registers
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int mblk = item / NS, ns = item % NS;
+      for (int item = worker; item < n_items; item += n_workers) {
+        const int mblk = item_mblk(item), ns = item % NS;
         const int t_begin = ns * tiles_per_item;
         const int t_end = min(n_tiles, t_begin + tiles_per_item);
         for (int t = t_begin; t < t_end; ++t) {
@@ -326,7 +339,11 @@ vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             ptx::mbar_wait(&empty[stage], phase ^ 1);
             ptx::mbar_expect_tx(&full[stage], L::A_BYTES + L::B_BYTES);
             ptx::tma_load_2d(sA + stage * L::A_BYTES, &tmX, &full[stage], kb * VQ_BK, mblk * VQ_BM);
-            ptx::tma_load_2d(sB + stage * L::B_BYTES, &tmC, &full[stage], kb * VQ_BK, t * VQ_BN);
+            if constexpr (CL == 2)   // this CTA's half of the codebook tile, into both CTAs
+              ptx::tma_load_2d_multicast(sB + stage * L::B_BYTES + rank * (L::B_BYTES / 2), &tmC, &full[stage], kb * VQ_BK,
+                                         t * VQ_BN + rank * (VQ_BN / 2), (uint16_t)3);
+            else
+              ptx::tma_load_2d(sB + stage * L::B_BYTES, &tmC, &full[stage], kb * VQ_BK, t * VQ_BN);
             if (++stage == VQ_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -337,7 +354,7 @@ vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (ptx::elect_one()) {  // one lane, known to the compiler: operands go to uniform registers
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = worker; item < n_items; item += n_workers) {
         const int ns = item % NS;
         const int t_begin = ns * tiles_per_item;
         const int t_end = min(n_tiles, t_begin + tiles_per_item);
@@ -358,7 +375,8 @@ vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               ptx::mma_bf16_ss(tmem_base, da0, db, IDESC, acc);
               ptx::mma_bf16_ss(tmem_base + VQ_BN, da1, db, IDESC, acc);
             }
-            ptx::mma_commit(&empty[stage]);
+            if constexpr (CL == 2) ptx::mma_commit_multicast(&empty[stage], (uint16_t)3);
+            else ptx::mma_commit(&empty[stage]);
             if (++stage == VQ_STAGES) { stage = 0; phase ^= 1; }
           }
           ptx::mma_commit(tfull);
@@ -372,8 +390,8 @@ vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int half = (warp - 2) >> 2;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + half * VQ_BN;
     uint32_t tphase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int mblk = item / NS, ns = item % NS;
+    for (int item = worker; item < n_items; item += n_workers) {
+      const int mblk = item_mblk(item), ns = item % NS;
       const int t_begin = ns * tiles_per_item;
       const int t_end = min(n_tiles, t_begin + tiles_per_item);
       const int row = mblk * VQ_BM + half * 128 + q * 32 + lane;
@@ -425,6 +443,7 @@ vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) ptx::cluster_sync();   // no CTA exits while its peer may still multicast into it
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
@@ -657,7 +676,7 @@ __global__ void vq_exhaustive_write_kernel(const int* __restrict__ ovf_rows, con
 int launch_vq_search(const void* x, int x_dt, const float* x2_opt, int64_t nrows, int D, const float* codebook_f32,
                      const __nv_bfloat16* codebook_bf16, const float* c2, const float* c2max_dev, int K,
                      int64_t* codes, void* ws, size_t ws_bytes, float window_factor, bool use_tc, bool x2_exact,
-                     cudaStream_t st, int sm_count, int* stats_host_opt) {
+                     cudaStream_t st, int sm_count, int* stats_host_opt, int cta_pairs) {
   if (nrows == 0) return DC_OK;
   DC_CHECK(nrows < (1ll << 31) - VQ_BM, DC_ERR_SHAPE, "vq_search: too many rows (%lld)", (long long)nrows);
   DC_CHECK(D % 64 == 0, DC_ERR_SHAPE, "vq_search: D=%d must be a multiple of 64", D);
@@ -712,7 +731,9 @@ int launch_vq_search(const void* x, int x_dt, const float* x2_opt, int64_t nrows
       }
     }
     const int tiles_per_item = (n_tiles + NS - 1) / NS;
-    const int n_items = n_mblk * NS;
+    const bool pair = cta_pairs == 2 && n_mblk >= 2 && sm_count >= 2;
+    const int CLv = pair ? 2 : 1;
+    const int n_items = ((n_mblk + CLv - 1) / CLv) * NS;   // pair items: two row blocks x one codebook split
     CUtensorMap tmX, tmC;
     {
       const uint64_t dims[2] = {(uint64_t)D, (uint64_t)nrows};
@@ -723,19 +744,38 @@ int launch_vq_search(const void* x, int x_dt, const float* x2_opt, int64_t nrows
     {
       const uint64_t dims[2] = {(uint64_t)D, (uint64_t)K};
       const uint64_t strides[1] = {(uint64_t)D * 2};
-      const uint32_t box[2] = {VQ_BK, VQ_BN};
+      const uint32_t box[2] = {VQ_BK, (uint32_t)(VQ_BN / CLv)};   // pairs: each CTA loads half the codes of a tile
       DC_TRY(make_tmap_bf16(&tmC, codebook_bf16, 2, dims, strides, box, 128));
     }
     static std::atomic<unsigned> attr_dev_mask{0u};  // once per (function, device); atomic because host threads driving different devices meet here
     int dev = 0;
     DC_CUDA(cudaGetDevice(&dev));
     if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
-      DC_CUDA(cudaFuncSetAttribute(vq_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VqSmem::TOTAL));
+      DC_CUDA(cudaFuncSetAttribute(vq_score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, VqSmem::TOTAL));
+      DC_CUDA(cudaFuncSetAttribute(vq_score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, VqSmem::TOTAL));
       attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
     }
-    const int grid = n_items < sm_count ? n_items : sm_count;
-    vq_score_kernel<<<grid, VQ_THREADS, VqSmem::TOTAL, st>>>(tmX, tmC, c2, w.win, w.best, w.cnt, w.cand, (int)nrows,
-                                                             n_items, NS, n_tiles, tiles_per_item, D / VQ_BK);
+    const int workers = n_items < sm_count / CLv ? n_items : sm_count / CLv;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(workers * CLv));
+    cfg.blockDim = dim3(VQ_THREADS);
+    cfg.dynamicSmemBytes = VqSmem::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLv;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pair ? 1 : 0;
+    const int kblocks = D / VQ_BK, nr = (int)nrows;
+    if (pair)
+      DC_CUDA(cudaLaunchKernelEx(&cfg, vq_score_kernel<2>, tmX, tmC, c2, (const float*)w.win, w.best, w.cnt, w.cand, nr, n_items,
+                                 NS, n_tiles, tiles_per_item, kblocks));
+    else
+      DC_CUDA(cudaLaunchKernelEx(&cfg, vq_score_kernel<1>, tmX, tmC, c2, (const float*)w.win, w.best, w.cnt, w.cand, nr, n_items,
+                                 NS, n_tiles, tiles_per_item, kblocks));
   } else {
     DC_CHECK((size_t)D * 4 <= 48 * 1024, DC_ERR_SHAPE, "vq_search: D=%d too large for the CUDA-core scorer", D);
     vq_score_simt_kernel<<<(unsigned)nrows, 256, (size_t)D * 4, st>>>(xb, codebook_bf16, c2, w.win, w.best, w.cnt,

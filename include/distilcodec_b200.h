@@ -79,7 +79,8 @@ int dc_destroy(dc_handle h);
  * (0 [default] = ||x||^2 summed in the order of the reference's CPU path, ATen cascade_sum; 1 = correctly rounded),
  * "fuse_pairs" (1 [default] = the narrow decoder stages run each conv1 -> SiLU -> conv2 step as one kernel),
  * "pairx" (which fused kernel the C = 32 stage uses: 0 conv_ws_pair, 1 conv_pair on the fp32 stream, 2 [default]
- * conv_pair with the bf16 side buffer). */
+ * conv_pair with the bf16 side buffer), "cta_pairs" (2 [default] = the tensor-bound kernels run as thread-block clusters of
+ * two CTAs that TMA-multicast the weight / codebook tiles they share; 1 = single CTAs; results are bit-identical). */
 int dc_set_option(dc_handle h, const char* key, double value);
 
 /* Weight ingestion.  Replaces `load_state_dict` on the three modules (distil_codec.py:91-94): call once per

@@ -128,13 +128,21 @@ PAIR_CASES = [
     (1, 641, 512, 1024, 3, 1, 0, False),    # 6 row tiles (ragged last), four N blocks
     (5, 128, 256, 512, 7, 3, 2, False),     # 5 single-tile clips: pairs straddle clips
     (1, 100, 256, 256, 3, 1, 0, False),     # one row tile: falls back to single CTAs
+    (3, 97, 256, 1024, 1, 1, 1, False),     # J = 1 (gemm_tc): pwconv1 + GELU, clips flattened, 3 row tiles (ghost)
+    (3, 97, 1024, 256, 1, 1, 0, True),      # pwconv2 + residual
+    (2, 140, 1024, 1024, 13, 1, 0, False),  # conv_pre k13
+    (1, 1, 1024, 3584, 1, 1, 0, False),     # a single frame: single CTAs
+    (1, 515, 128, 128, 7, 3, 2, False),     # C = N = 128 (conv_ts): 3 tiles of 256 rows (ghost)
+    (3, 300, 128, 128, 11, 5, 0, True),     # ... 6 tiles, residual
+    (2, 256, 128, 128, 3, 1, 2, False),     # ... the k = 3 variant (third activation buffer)
 ]
 
 
 @pytest.mark.parametrize("case", PAIR_CASES, ids=lambda c: "B%dT%dC%dN%dk%dd%da%dr%d" % tuple(int(v) for v in c))
 def test_wide_conv_cta_pairs_with_weight_multicast(case):
-    """conv_tsw as clusters of two CTAs that TMA-multicast the weight tiles (option "tsw_cluster" = 2) against the same
-    kernel as single CTAs and against torch: the MMA sequence per tile is unchanged, so the results are bit-identical."""
+    """conv_tsw / gemm_tc / conv_ts as clusters of two CTAs that TMA-multicast the weight tiles (option "cta_pairs" = 2) against
+    the same kernels as single CTAs and against torch: the MMA sequence per tile is unchanged, so the results are
+    bit-identical."""
     B, T, C, N, k, dil, act, with_res = case
     eng = engine("W1", "bf16", 1024)
     a = _rand(B, T, C, seed=11)
@@ -149,10 +157,10 @@ def test_wide_conv_cta_pairs_with_weight_multicast(case):
     outs = {}
     try:
         for cl in (1, 2):
-            eng.set_option("tsw_cluster", cl)
+            eng.set_option("cta_pairs", cl)
             outs[cl] = eng.op_conv_gemm(*args)
             torch.cuda.synchronize()
     finally:
-        eng.set_option("tsw_cluster", 2)
+        eng.set_option("cta_pairs", 2)
     assert rel_err(outs[2], ref) < TOL["bf16"]
     assert torch.equal(outs[1], outs[2])

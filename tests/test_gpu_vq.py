@@ -115,3 +115,23 @@ def test_full_config2_size_properties():
     assert (codes == gidx).float().mean().item() == 1.0
     part = torch.cat([eng.vq_search(x[:30000].contiguous()), eng.vq_search(x[30000:].contiguous())])
     assert torch.equal(part, codes)
+
+
+@pytest.mark.parametrize("n", [257, 600, 4096])
+def test_cta_pairs_sharing_codebook_tiles_give_identical_codes(n):
+    """vq_score as clusters of two CTAs that TMA-multicast the codebook tiles (option "cta_pairs" = 2) vs single CTAs:
+    same candidates, same codes; odd block counts run a ghost block."""
+    eng = engine("W0", "bf16")
+    x = make_vq_rows(n, kind="bf16", seed=21).to(eng.device).to(torch.bfloat16)
+    out = {}
+    try:
+        for cl in (1, 2):
+            eng.set_option("cta_pairs", cl)
+            out[cl], st = eng.vq_search(x, stats=True)
+            assert st["rows"] == n
+    finally:
+        eng.set_option("cta_pairs", 2)
+    assert torch.equal(out[1], out[2])
+    E = state_dict("W0")["quantizer.grvq.rvqs.0.layers.0._codebook.embed"][0]
+    bad = (out[2].cpu() != R.vq_search(x.float().cpu(), E)).sum().item()
+    assert bad <= max(1, n // 1000)
