@@ -70,7 +70,7 @@ static VqWs vq_carve(void* base, int64_t rows, int D, bool need_xb) {
     off += align_up(bytes, 256);
     return r;
   };
-  w.xb = reinterpret_cast<__nv_bfloat16*>(take(need_xb ? (size_t)rows * D * 2 : 0));
+  w.xb = reinterpret_cast<__nv_bfloat16*>(take(need_xb ? (size_t)rows * D * 4 : 0));   // fp32 rows: [hi | lo] bf16 split
   w.x2e = reinterpret_cast<float*>(take((size_t)rows * 4));
   w.win = reinterpret_cast<float*>(take((size_t)rows * 4));
   w.best = reinterpret_cast<float*>(take((size_t)rows * VQ_NS_MAX * 4));
@@ -162,12 +162,19 @@ __global__ void __launch_bounds__(256) vq_prep_kernel(const void* __restrict__ x
     }
   } else {
     const float* p = reinterpret_cast<const float*>(x) + (size_t)row * D;
-    __nv_bfloat16* o = xb + (size_t)row * D;
+    // Full-precision rows are scored as a two-term bf16 split x = hi + lo + r (K-extended GEMM: [hi | lo] against the
+    // codebook tile twice), so that the rounding of x itself (|r| <= 2^-17 |x|) all but vanishes from the candidate
+    // window; with hi alone ~1 % of the W0 rows overflowed the candidate lists into the exhaustive pass (11 % of the
+    // fp32-mode step).
+    __nv_bfloat16* o = xb + (size_t)row * 2 * D;
     for (int i = lane; i < D; i += 32) {
       const float v = __ldg(p + i);
-      const __nv_bfloat16 b = __float2bfloat16_rn(v);
-      o[i] = b;
-      const float d = v - __bfloat162float(b);   // exact (Sterbenz): the rounding residual of this element
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const float r1 = v - __bfloat162float(hi);            // exact (Sterbenz)
+      const __nv_bfloat16 lo = __float2bfloat16_rn(r1);
+      o[i] = hi;
+      o[D + i] = lo;
+      const float d = r1 - __bfloat162float(lo);            // exact: what the split does not represent
       dx2 = fmaf(d, d, dx2);
     }
 #pragma unroll
@@ -193,9 +200,11 @@ __global__ void __launch_bounds__(256) vq_prep_kernel(const void* __restrict__ x
     // (dc_finalize).  Those are ~0.3 of the generic 2^-8 |v| bound, which is why a window of 2 e is both rigorous and
     // small enough for the 32-slot candidate lists on every weight set of the tests.  window_factor scales it
     // (option "vq_window", 1.0 = this bound); 6 ulp(d^2) cover the fp32 evaluation of the reference's own expression.
+    // Full-precision rows are scored as the two-term split above: x~ = hi + lo, ||x - x~|| <= 2^-17 ||x||.
     const float c2max = c2max_p[0], r2max = c2max_p[1];
-    const float xn = sqrtf(x2) * 1.0001f, cn = sqrtf(c2max), dx = sqrtf(dx2) * 1.001f, rn = sqrtf(r2max) * 1.001f;
-    const float e_acc = 2.f * (float)D * 1.1920929e-7f * xn * cn;   // fp32 accumulation over D products
+    const float xn = sqrtf(x2) * 1.005f /* ||hi|| + ||lo|| */, cn = sqrtf(c2max), dx = sqrtf(dx2) * 1.001f,
+                rn = sqrtf(r2max) * 1.001f;
+    const float e_acc = 2.f * (float)D * (X_BF16 ? 1.f : 2.f) * 1.1920929e-7f * xn * cn;   // fp32 accumulation over D (2 D) products
     const float e = 2.f * (dx * cn + xn * rn) + e_acc;
     const float dmax2 = x2 + c2max + 2.f * xn * cn;     // upper bound of the reference's d^2
     int ex = 0;
@@ -280,7 +289,8 @@ __global__ void __launch_bounds__(VQ_THREADS, 1)
 vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmC,
                 const float* __restrict__ c2, const float* __restrict__ win, float* __restrict__ best_out,
                 int* __restrict__ cnt_out, int2* __restrict__ cand_out, int nrows, int n_items, int NS,
-                int n_tiles, int tiles_per_item, int kblocks) {
+                int n_tiles, int tiles_per_item, int kblocks, int kblocks_c /*K blocks of the codebook: kblocks, or
+                kblocks / 2 when the rows are a [hi | lo] split*/) {
   using L = VqSmem;
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, VQ_BN);
   extern __shared__ uint8_t smem_raw[];
@@ -340,10 +350,10 @@ vq_score_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             ptx::mbar_expect_tx(&full[stage], L::A_BYTES + L::B_BYTES);
             ptx::tma_load_2d(sA + stage * L::A_BYTES, &tmX, &full[stage], kb * VQ_BK, mblk * VQ_BM);
             if constexpr (CL == 2)   // this CTA's half of the codebook tile, into both CTAs
-              ptx::tma_load_2d_multicast(sB + stage * L::B_BYTES + rank * (L::B_BYTES / 2), &tmC, &full[stage], kb * VQ_BK,
-                                         t * VQ_BN + rank * (VQ_BN / 2), (uint16_t)3);
+              ptx::tma_load_2d_multicast(sB + stage * L::B_BYTES + rank * (L::B_BYTES / 2), &tmC, &full[stage],
+                                         (kb % kblocks_c) * VQ_BK, t * VQ_BN + rank * (VQ_BN / 2), (uint16_t)3);
             else
-              ptx::tma_load_2d(sB + stage * L::B_BYTES, &tmC, &full[stage], kb * VQ_BK, t * VQ_BN);
+              ptx::tma_load_2d(sB + stage * L::B_BYTES, &tmC, &full[stage], (kb % kblocks_c) * VQ_BK, t * VQ_BN);
             if (++stage == VQ_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -458,11 +468,14 @@ __global__ void __launch_bounds__(256) vq_score_simt_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ c2,
                                                             const float* __restrict__ win,
                                                             float* __restrict__ best_out, int* __restrict__ cnt_out,
-                                                            int2* __restrict__ cand_out, int nrows, int K, int D) {
+                                                            int2* __restrict__ cand_out, int nrows, int K, int D,
+                                                            int split /*rows are [hi | lo] bf16 splits of fp32 rows*/) {
   extern __shared__ float sx[];  // D floats: the row
   __shared__ float s_scores[256];
   const int row = blockIdx.x;
-  for (int i = threadIdx.x; i < D; i += 256) sx[i] = __bfloat162float(xb[(size_t)row * D + i]);
+  const size_t pitch = (size_t)D * (split ? 2 : 1);
+  for (int i = threadIdx.x; i < D; i += 256)
+    sx[i] = __bfloat162float(xb[row * pitch + i]) + (split ? __bfloat162float(xb[row * pitch + D + i]) : 0.f);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float best = INFINITY;
@@ -736,8 +749,9 @@ int launch_vq_search(const void* x, int x_dt, const float* x2_opt, int64_t nrows
     const int n_items = ((n_mblk + CLv - 1) / CLv) * NS;   // pair items: two row blocks x one codebook split
     CUtensorMap tmX, tmC;
     {
-      const uint64_t dims[2] = {(uint64_t)D, (uint64_t)nrows};
-      const uint64_t strides[1] = {(uint64_t)D * 2};
+      const uint64_t Dx = (uint64_t)D * (xb16 ? 1 : 2);   // fp32 rows were split into [hi | lo]
+      const uint64_t dims[2] = {Dx, (uint64_t)nrows};
+      const uint64_t strides[1] = {Dx * 2};
       const uint32_t box[2] = {VQ_BK, VQ_BM};
       DC_TRY(make_tmap_bf16(&tmX, xb, 2, dims, strides, box, 128));
     }
@@ -769,17 +783,17 @@ int launch_vq_search(const void* x, int x_dt, const float* x2_opt, int64_t nrows
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pair ? 1 : 0;
-    const int kblocks = D / VQ_BK, nr = (int)nrows;
+    const int kblocks_c = D / VQ_BK, kblocks = kblocks_c * (xb16 ? 1 : 2), nr = (int)nrows;
     if (pair)
       DC_CUDA(cudaLaunchKernelEx(&cfg, vq_score_kernel<2>, tmX, tmC, c2, (const float*)w.win, w.best, w.cnt, w.cand, nr, n_items,
-                                 NS, n_tiles, tiles_per_item, kblocks));
+                                 NS, n_tiles, tiles_per_item, kblocks, kblocks_c));
     else
       DC_CUDA(cudaLaunchKernelEx(&cfg, vq_score_kernel<1>, tmX, tmC, c2, (const float*)w.win, w.best, w.cnt, w.cand, nr, n_items,
-                                 NS, n_tiles, tiles_per_item, kblocks));
+                                 NS, n_tiles, tiles_per_item, kblocks, kblocks_c));
   } else {
     DC_CHECK((size_t)D * 4 <= 48 * 1024, DC_ERR_SHAPE, "vq_search: D=%d too large for the CUDA-core scorer", D);
     vq_score_simt_kernel<<<(unsigned)nrows, 256, (size_t)D * 4, st>>>(xb, codebook_bf16, c2, w.win, w.best, w.cnt,
-                                                                       w.cand, (int)nrows, K, D);
+                                                                       w.cand, (int)nrows, K, D, xb16 ? 0 : 1);
   }
   }
   ++g_launches_vq;
