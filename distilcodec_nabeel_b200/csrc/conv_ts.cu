@@ -538,6 +538,9 @@ int launch_conv_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGe
   // CTA pairs (weight multicast) need at least one full pair of row tiles and an even share of the SMs
   const bool pair = s.cluster == 2 && (long long)s.B * ((s.T + 127) / 128) >= 2 && sm_count >= 2;
   if (e.res || (e.out0 && e.out1)) {
+#ifdef DC_TSW_RES_CW32   // A/B builds: whole-line epilogue chunks + 3-stage ring for every residual layer
+    if (pair) return launch_tsw<2, 32, 3, 2>(A, W, s, e, st, sm_count);
+#endif
     if (s.J * s.C <= 1792 && s.N == 256)
       return pair ? launch_tsw<2, 32, 3, 2>(A, W, s, e, st, sm_count) : launch_tsw<2, 32, 3, 1>(A, W, s, e, st, sm_count);
     return pair ? launch_tsw<2, 16, 4, 2>(A, W, s, e, st, sm_count) : launch_tsw<2, 16, 4, 1>(A, W, s, e, st, sm_count);
