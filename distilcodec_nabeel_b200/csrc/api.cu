@@ -114,7 +114,8 @@ struct Dense {  // one shifted-row implicit GEMM layer
   int phase_cols = 0;               // ConvTranspose1d: output columns per stride phase
   uint32_t zero_taps = 0;           // bit (phase*J + j): tap j is all-zero for that phase
   __nv_bfloat16* w_bf16 = nullptr;  // [N][J*C]   (DC_MODE_BF16)
-  float* w_f32 = nullptr;           // [J*C][N]   (DC_MODE_FP32)
+  float* w_f32 = nullptr;           // [J*C][N]   (DC_MODE_FP32, CUDA-core kernel)
+  __nv_bfloat16* w_f32x = nullptr;  // [N][J][2C] (DC_MODE_FP32, tensor-core kernel: two-term bf16 split per tap, gemm_f32x.cu)
   const float* bias = nullptr;      // [N]
   // block-Toeplitz "phase form" for the C = 32 ResBlock convs with dilation 1 (conv_pair.cu): one accumulator row =
   // two time steps, W[(r, co)][(o, ci)] = w[co, ci, tap o - r] (zero outside 0..J-1), and the bias repeated twice
@@ -161,6 +162,11 @@ struct dc_handle_s {
   // 2: the tensor-bound kernels whose CTAs stream the same weight / codebook tiles (conv_tsw, gemm_tc with N tiles of 256,
   // vq_score) run as CTA pairs (thread-block clusters) that TMA-multicast those tiles to each other; 1: single CTAs
   int tsw_cluster = 2;
+  // DC_MODE_FP32: dense layers on the tensor cores (split-bf16 operands, chunked fp32 accumulation, gemm_f32x.cu);
+  // 0 = the CUDA-core kernel (gemm_f32.cu)
+  bool fp32_tc = true;
+  mutable __nv_bfloat16* split_scratch = nullptr;   // (rows, 2C) bf16 split of a layer's fp32 input; set per stage call
+  mutable size_t split_cap = 0;                     // ... capacity in elements
   int epi_prefetch = 1;
 
   // encoder
@@ -217,6 +223,8 @@ static void reset_packed(dc_handle_s* h) {
         for (auto& d : c) d = Dense();
   h->post_w = nullptr;
   h->post_C = 0;
+  h->split_scratch = nullptr;
+  h->split_cap = 0;
 }
 
 static int run_dense(const dc_handle_s* h, const struct Dense& d, const void* A, int B, int T, Epilogue ep, cudaStream_t st);
@@ -299,6 +307,12 @@ static int pack_dense(dc_handle_s* h, const float* src, bool transposed, int O, 
   } else {
     DC_TRY(dev_alloc(h, &d->w_f32, elems));
     DC_TRY(launch_pack_weight(src, pd, d->w_f32, nullptr, st));
+    if (d->C % 32 == 0 && d->N % 32 == 0) {  // tensor-core form: [N][J][hi C | mid C]
+      PackDesc ps = pd;
+      ps.split = 1;
+      DC_TRY(dev_alloc(h, &d->w_f32x, 2 * elems));
+      DC_TRY(launch_pack_weight(src, ps, nullptr, d->w_f32x, st));
+    }
   }
   if (bias && transposed && stride > 1) {
     float* b = nullptr;
@@ -387,6 +401,11 @@ static int run_dense(const dc_handle_s* h, const Dense& d, const void* A, int B,
   ep.prefetch = h->epi_prefetch;
   if (h->mode == DC_MODE_BF16)
     return launch_gemm_tc(reinterpret_cast<const __nv_bfloat16*>(A), d.w_bf16, s, ep, st, h->sm_count);
+  const size_t a_elems = (size_t)B * T * d.C;
+  if (h->fp32_tc && d.w_f32x && h->split_scratch && 2 * a_elems <= h->split_cap && gemm_f32x_supported(s)) {
+    DC_TRY(launch_split_f32(reinterpret_cast<const float*>(A), h->split_scratch, (size_t)B * T, d.C, st));
+    return launch_gemm_f32x(h->split_scratch, d.w_f32x, s, ep, st, h->sm_count);
+  }
   return launch_gemm_f32(reinterpret_cast<const float*>(A), d.w_f32, s, ep, st);
 }
 
@@ -458,6 +477,20 @@ static int run_block(const dc_handle_s* h, const Block& blk, float* x, void* a, 
 }
 
 // ---- stages ---------------------------------------------------------------------------------------------
+// fp32 mode: scratch for the [hi | mid] bf16 split of the largest fp32 operand a stage hands to a dense layer (the
+// tensor-core fp32 kernel splits every layer's input into it, gemm_f32x.cu).  Always part of the fp32-mode plan, whatever
+// the "fp32_tc" option says at the time.
+static void bind_split_scratch(const dc_handle_s* h, Arena& ar, size_t max_input_elems, bool dry) {
+  h->split_scratch = nullptr;
+  h->split_cap = 0;
+  if (h->mode != DC_MODE_FP32) return;
+  void* p = ar.get(max_input_elems * 2 * sizeof(__nv_bfloat16));
+  if (!dry) {
+    h->split_scratch = reinterpret_cast<__nv_bfloat16*>(p);
+    h->split_cap = max_input_elems * 2;
+  }
+}
+
 static int stage_encoder(const dc_handle_s* h, const float* mel_ncl, int B, int T, float* enc_out, Arena& ar, bool dry,
                          cudaStream_t st) {
   const size_t rows = (size_t)B * T, es = act_es(h);
@@ -469,6 +502,7 @@ static int stage_encoder(const dc_handle_s* h, const float* mel_ncl, int B, int 
   float* x = reinterpret_cast<float*>(ar.get(rows * maxdim * 4));
   void* a = ar.get(rows * maxdim * es);
   void* hid = ar.get(rows * maxdim * 4 * es);  // also holds the fp32 stem output before its LayerNorm
+  bind_split_scratch(h, ar, rows * (size_t)maxdim * 4, dry);
   if (dry) return DC_OK;
 
   DC_TRY(launch_transpose_ncl_to_nlc(mel_ncl, mel, ad, B, c.n_mels, T, st));
@@ -527,6 +561,7 @@ static int stage_quantizer(const dc_handle_s* h, const float* enc, int B, int T,
   void* xin_tmp = (x_pjt_in && !dry) ? nullptr : ar.get(rows * CD * es);  // project_in rows: scratch if the caller does not want them
   const size_t vq_bytes = vq_workspace_bytes((int64_t)rows, CD, ad == DT_BF16);
   void* vq_ws = ar.get(vq_bytes);
+  bind_split_scratch(h, ar, rows * (size_t)(4 * D > CD ? 4 * D : CD), dry);
   if (dry) return DC_OK;
 
   const void* a0 = enc;
@@ -574,6 +609,7 @@ static int stage_decode_codes(const dc_handle_s* h, const int64_t* codes, int B,
   void* hid = ar.get(rows * D * 4 * es);
   void* qd = ar.get(rows * D * es);
   void* fup_op = ar.get(rows * CD * es);
+  bind_split_scratch(h, ar, rows * (size_t)(4 * D > CD ? 4 * D : CD), dry);
   if (dry) return DC_OK;
   if (h->mode == DC_MODE_BF16)
     DC_TRY(launch_gather_rows(h->codebook, codes, (int64_t)rows, CD, h->K, nullptr,
@@ -616,6 +652,10 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
   }
   void* carry[2] = {ar.get((size_t)B * max_elems * es), ar.get((size_t)B * max_elems * es)};
   void* zop = h->mode == DC_MODE_BF16 ? ar.get((size_t)B * T * Din * 2) : nullptr;
+  {
+    const size_t in0 = (size_t)T * Din;
+    bind_split_scratch(h, ar, (size_t)B * (in0 > max_elems ? in0 : max_elems), dry);
+  }
   const size_t m0 = ar.mark();
 
   if (!dry) {
@@ -858,6 +898,8 @@ int dc_set_option(dc_handle h, const char* key, double value) {
   } else if (!strcmp(key, "cta_pairs") || !strcmp(key, "tsw_cluster")) {
     DC_CHECK(value == 1.0 || value == 2.0, DC_ERR_ARG, "cta_pairs must be 1 or 2");
     h->tsw_cluster = (int)value;
+  } else if (!strcmp(key, "fp32_tc")) {
+    h->fp32_tc = value != 0.0;
   } else if (!strcmp(key, "pairx")) {
     DC_CHECK(value == 0.0 || value == 1.0 || value == 2.0, DC_ERR_ARG, "pairx must be 0, 1 or 2");
     h->pairx = (int)value;
@@ -1258,6 +1300,29 @@ int dc_op_conv_gemm(dc_handle h, const float* a_dev, const float* w_dev, const f
       set_error("dc_op_conv_gemm: %s", cudaGetErrorString(ce));
       rc = DC_ERR_CUDA;
     }
+  } else if (h->fp32_tc && gemm_f32x_supported(s) && J <= 128) {
+    // fp32 mode on the tensor cores: split both operands into [hi | mid] bf16 (gemm_f32x.cu)
+    __nv_bfloat16 *a2 = nullptr, *w2 = nullptr;
+    DC_CUDA(cudaMalloc(reinterpret_cast<void**>(&a2), na * 4));
+    if (cudaMalloc(reinterpret_cast<void**>(&w2), nw * 4) != cudaSuccess) {
+      cudaFree(a2);
+      set_error("dc_op_conv_gemm: out of memory");
+      return DC_ERR_CUDA;
+    }
+    PackDesc pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.N = N; pd.J = J; pd.C = C; pd.phases = 1; pd.s_n = (long long)J * C; pd.s_c = 1; pd.s_k = C; pd.split = 1;
+    for (int j = 0; j < J; ++j) pd.kmap[j] = j;
+    rc = launch_pack_weight(w_dev, pd, nullptr, w2, st);
+    if (!rc) rc = launch_split_f32(a_dev, a2, (size_t)B * T, C, st);
+    if (!rc) rc = launch_gemm_f32x(a2, w2, s, e, st, h->sm_count);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    cudaFree(a2);
+    cudaFree(w2);
+    if (!rc && ce != cudaSuccess) {
+      set_error("dc_op_conv_gemm: %s", cudaGetErrorString(ce));
+      rc = DC_ERR_CUDA;
+    }
   } else {
     float* wt = nullptr;
     DC_CUDA(cudaMalloc(reinterpret_cast<void**>(&wt), nw * 4));
@@ -1365,7 +1430,7 @@ int dc_profile_collect(dc_profile_row* rows, int cap, int* n) {
 uint64_t dc_launch_count(void) {
   return g_launches_api + gemm_tc_launch_count() + gemm_f32_launch_count() + pointwise_launch_count() +
          vq_launch_count() + conv_ws_launch_count() + mel_launch_count() + conv_ts_launch_count() +
-         conv_pairx_launch_count();
+         conv_pairx_launch_count() + gemm_f32x_launch_count();
 }
 
 }  // extern "C"

@@ -131,6 +131,13 @@ __device__ __forceinline__ void epilogue_store(const Epilogue& e, size_t row, in
 // ---------------------------------------------------------------- launchers implemented across the .cu files
 // fp32 CUDA-core implicit GEMM.  A fp32 (B,T,C); W fp32 [J*C][N] (N contiguous).
 int launch_gemm_f32(const float* A, const float* W, const ConvGemmShape& s, const Epilogue& e, cudaStream_t st);
+// fp32-accurate tensor-core implicit GEMM (gemm_f32x.cu): A2 bf16 (B,T,2C) = [hi | mid] split of the fp32 activations
+// (launch_split_f32), W2 bf16 [N][J][2C] = the same split of the weights; chunked accumulation, fp32 epilogue.
+bool gemm_f32x_supported(const ConvGemmShape& s);
+int launch_split_f32(const float* in, __nv_bfloat16* out, size_t rows, int C, cudaStream_t st);
+int launch_gemm_f32x(const __nv_bfloat16* A2, const __nv_bfloat16* W2, const ConvGemmShape& s, const Epilogue& e,
+                     cudaStream_t st, int sm_count);
+uint64_t gemm_f32x_launch_count();
 // bf16 tcgen05 implicit GEMM.  A bf16 (B,T,C); W bf16 [N][J*C] (K contiguous).
 int launch_gemm_tc(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGemmShape& s, const Epilogue& e,
                    cudaStream_t st, int sm_count);
@@ -181,6 +188,7 @@ struct PackDesc {
   int phases;             // N = phases * n_inner
   long long s_n, s_c, s_k;  // source strides (elements) for (n_inner, c, kernel tap)
   int kmap[8 * 16];       // kmap[phase*J + j] = source kernel tap or -1 (zero)
+  int split;              // 1: the bf16 output is [N][J][2C], channels [0,C) = bf16(w), [C,2C) = bf16(w - bf16(w)) (gemm_f32x.cu)
 };
 int launch_pack_weight(const float* src, const PackDesc& d, float* out_kn_f32 /*nullable*/,
                        __nv_bfloat16* out_nk_bf16 /*nullable*/, cudaStream_t st);

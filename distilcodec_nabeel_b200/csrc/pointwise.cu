@@ -628,15 +628,21 @@ int launch_weight_norm_fold(const float* g, const float* v, float* w, int dim0, 
 //   Wp[n][j*C + c],  n = phase * n_inner + ni,  source = src[ni*s_n + c*s_c + kmap[phase][j]*s_k] (0 if kmap < 0)
 __global__ void pack_weight_kernel(const float* __restrict__ src, PackDesc d, float* __restrict__ o_kn,
                                    __nv_bfloat16* __restrict__ o_nk) {
-  const long long K = (long long)d.J * d.C, total = K * d.N;
+  const int Cx = d.split ? 2 * d.C : d.C;   // packed channels per tap
+  const long long K = (long long)d.J * Cx, total = K * d.N;
   const int n_inner = d.N / d.phases;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(i / K);
     const int k = (int)(i % K);
-    const int j = k / d.C, c = k % d.C;
+    const int j = k / Cx, cx = k % Cx, c = cx % d.C;
     const int ph = n / n_inner, ni = n % n_inner;
     const int kk = d.kmap[ph * d.J + j];
     const float v = kk < 0 ? 0.f : src[ni * d.s_n + c * d.s_c + kk * d.s_k];
+    if (d.split) {  // two-term bf16 split of the fp32 weight: hi, then what hi leaves
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      o_nk[(size_t)n * K + k] = cx < d.C ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+      continue;
+    }
     if (o_kn) o_kn[(size_t)k * d.N + n] = v;
     if (o_nk) o_nk[(size_t)n * K + k] = __float2bfloat16_rn(v);
   }

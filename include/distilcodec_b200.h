@@ -80,7 +80,9 @@ int dc_destroy(dc_handle h);
  * "fuse_pairs" (1 [default] = the narrow decoder stages run each conv1 -> SiLU -> conv2 step as one kernel),
  * "pairx" (which fused kernel the C = 32 stage uses: 0 conv_ws_pair, 1 conv_pair on the fp32 stream, 2 [default]
  * conv_pair with the bf16 side buffer), "cta_pairs" (2 [default] = the tensor-bound kernels run as thread-block clusters of
- * two CTAs that TMA-multicast the weight / codebook tiles they share; 1 = single CTAs; results are bit-identical). */
+ * two CTAs that TMA-multicast the weight / codebook tiles they share; 1 = single CTAs; results are bit-identical),
+ * "fp32_tc" (DC_MODE_FP32 only: 1 [default] = dense layers on the tensor cores with split-bf16 operands and chunked fp32
+ * accumulation, 0 = the CUDA-core fp32 kernel). */
 int dc_set_option(dc_handle h, const char* key, double value);
 
 /* Weight ingestion.  Replaces `load_state_dict` on the three modules (distil_codec.py:91-94): call once per

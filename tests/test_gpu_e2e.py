@@ -309,3 +309,30 @@ def test_fp32_stream_pair_kernel_matches_oracle_and_the_two_kernel_form(variant)
         for form in (1, 2):
             assert rel_err(outs[form], ref) < TOL["bf16"], (B, T, form)
             assert rel_err(outs[form], outs[0]) < 2e-4, (B, T, form)   # only the summation order differs
+
+
+@pytest.mark.parametrize("variant", ["W0", "W1"])
+def test_fp32_mode_on_tensor_cores_keeps_the_fp32_gate(variant):
+    """DC_MODE_FP32 (the reference API's default, enable_bfloat16=False) with its dense layers on the tensor cores
+    (option "fp32_tc": two-term bf16 split of both operands, three cross products, accumulation chunked to K <= 256 per
+    term and summed with round-to-nearest fp32 adds, gemm_f32x.cu) against the oracle, next to the CUDA-core fp32 kernel:
+    both inside 1e-4, the tensor-core form within a small factor of the CUDA-core one."""
+    sd = state_dict(variant)
+    eng = engine(variant, "fp32")
+    mel = make_mel(2, 130, seed=71)
+    z = make_latents(2, 61, seed=72) * 0.5
+    ref_enc = R.encoder_forward(sd, mel)
+    ref_wav = R.generator_forward(sd, z)[:, 0]
+    err = {}
+    try:
+        for tc in (1, 0):
+            eng.set_option("fp32_tc", tc)
+            enc = eng.encoder(mel.to(eng.device))
+            wav = eng.generator(z.transpose(1, 2).contiguous().to(eng.device))
+            err[tc] = (rel_err(enc.transpose(1, 2), ref_enc), rel_err(wav, ref_wav))
+    finally:
+        eng.set_option("fp32_tc", 1)
+    print(f"{variant} fp32 mode rel err (encoder, waveform): tensor cores {err[1][0]:.2e} {err[1][1]:.2e}; "
+          f"CUDA cores {err[0][0]:.2e} {err[0][1]:.2e}")
+    assert max(err[0]) < 1e-4 and max(err[1]) < 1e-4
+    assert max(err[1]) < 3e-5, err[1]                 # a 3x margin to the gate on both weight sets
