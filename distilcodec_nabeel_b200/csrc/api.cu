@@ -227,9 +227,15 @@ static void reset_packed(dc_handle_s* h) {
   h->split_cap = 0;
 }
 
-static int run_dense(const dc_handle_s* h, const struct Dense& d, const void* A, int B, int T, Epilogue ep, cudaStream_t st);
+static int run_dense(const dc_handle_s* h, const struct Dense& d, const void* A, int B, int T, Epilogue ep, cudaStream_t st,
+                     int a_dt = -1);
 static int act_dt(const dc_handle_s* h) { return h->mode == DC_MODE_BF16 ? DT_BF16 : DT_F32; }
 static size_t act_es(const dc_handle_s* h) { return h->mode == DC_MODE_BF16 ? 2 : 4; }
+// operand format of the decoder's conv -> conv chains: in fp32 mode on the tensor cores the producing epilogue writes the
+// two-term bf16 split the next layer's MMAs read (DT_SPLIT, 4 bytes per value like fp32), so no separate split pass runs
+static int gen_dt(const dc_handle_s* h) {
+  return h->mode == DC_MODE_BF16 ? DT_BF16 : (h->fp32_tc ? DT_SPLIT : DT_F32);
+}
 
 template <typename T>
 static int dev_alloc(dc_handle_s* h, T** out, size_t count) {
@@ -394,13 +400,20 @@ static int pack_block(dc_handle_s* h, const std::string& p, Block* blk, cudaStre
 }
 
 // ---- layer runners --------------------------------------------------------------------------------------
-static int run_dense(const dc_handle_s* h, const Dense& d, const void* A, int B, int T, Epilogue ep, cudaStream_t st) {
+// a_dt: format of A in fp32 mode (DT_F32 [default] or DT_SPLIT: already split by the producing epilogue)
+static int run_dense(const dc_handle_s* h, const Dense& d, const void* A, int B, int T, Epilogue ep, cudaStream_t st,
+                     int a_dt) {
   ConvGemmShape s{B, T, d.C, d.J, d.shift0, d.dil, d.N, d.alg_scale, d.phase_cols, d.zero_taps, h->tsw_cluster};
   if (!ep.bias) ep.bias = d.bias;
   ep.ldo = d.N;
+  ep.split_seg = d.phase_cols > 0 ? d.phase_cols : d.N;
   ep.prefetch = h->epi_prefetch;
   if (h->mode == DC_MODE_BF16)
     return launch_gemm_tc(reinterpret_cast<const __nv_bfloat16*>(A), d.w_bf16, s, ep, st, h->sm_count);
+  if (a_dt == DT_SPLIT) {
+    DC_CHECK(d.w_f32x && gemm_f32x_supported(s), DC_ERR_STATE, "split operand handed to a layer without tensor-core fp32 weights");
+    return launch_gemm_f32x(reinterpret_cast<const __nv_bfloat16*>(A), d.w_f32x, s, ep, st, h->sm_count);
+  }
   const size_t a_elems = (size_t)B * T * d.C;
   if (h->fp32_tc && d.w_f32x && h->split_scratch && 2 * a_elems <= h->split_cap && gemm_f32x_supported(s)) {
     DC_TRY(launch_split_f32(reinterpret_cast<const float*>(A), h->split_scratch, (size_t)B * T, d.C, st));
@@ -443,9 +456,9 @@ static int run_conv_pair(const dc_handle_s* h, const Dense& c1, const Dense& c2,
   Epilogue e1;  // xt = silu(c1(silu(x)))
   e1.act = ACT_SILU;
   e1.out0 = tb;
-  e1.out0_dt = act_dt(h);
-  DC_TRY(run_dense(h, c1, S, B, T, e1, st));
-  return run_dense(h, c2, tb, B, T, e2, st);
+  e1.out0_dt = gen_dt(h);
+  DC_TRY(run_dense(h, c1, S, B, T, e1, st, gen_dt(h)));
+  return run_dense(h, c2, tb, B, T, e2, st, gen_dt(h));
 }
 
 // x (fp32, B*T x C) <- x + gamma * pw2(gelu(pw1(LN(dwconv(x)))))     (convnext_utils.py:263-282)
@@ -455,11 +468,12 @@ static int run_block(const dc_handle_s* h, const Block& blk, float* x, void* a, 
                      void* out1_copy, bool dry, cudaStream_t st) {
   if (dry) return DC_OK;
   const int ad = act_dt(h);
+  const int hd = gen_dt(h);   // the hidden activation goes epilogue -> next GEMM: written in the operand format directly
   DC_TRY(launch_dwconv_ln(x, blk.dw_w, blk.dw_b, blk.ln_w, blk.ln_b, a, ad, B, T, blk.C, st));
   Epilogue e1;
   e1.act = ACT_GELU;
   e1.out0 = hid;
-  e1.out0_dt = ad;
+  e1.out0_dt = hd;
   DC_TRY(run_dense(h, blk.pw1, a, B, T, e1, st));
   Epilogue e2;
   e2.gamma = blk.gamma;
@@ -472,7 +486,7 @@ static int run_block(const dc_handle_s* h, const Block& blk, float* x, void* a, 
     e2.out1_dt = ad;
     e2.out1_silu = 0;
   }
-  DC_TRY(run_dense(h, blk.pw2, hid, B, T, e2, st));
+  DC_TRY(run_dense(h, blk.pw2, hid, B, T, e2, st, hd));
   return DC_OK;
 }
 
@@ -637,7 +651,7 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
                            cudaStream_t st) {
   const dc_config& c = h->cfg;
   const size_t es = act_es(h);
-  const int ad = act_dt(h);
+  const int ad = gen_dt(h);   // operand format of the conv chains (bf16 | fp32 | split), 2 or 4 bytes per value = act_es
   const int C0 = c.up_initial_channel, Din = h->conv_pre.C;
   // largest activation (elements per clip) over conv_pre output and every stage
   size_t max_elems = (size_t)T * C0;
@@ -688,7 +702,7 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
           Epilogue e;
           e.out0 = x;
           e.out0_dt = DT_F32;
-          DC_TRY(run_dense(h, h->ups[i], carry[cur], B, Lin, e, st));
+          DC_TRY(run_dense(h, h->ups[i], carry[cur], B, Lin, e, st, ad));
         }
         for (int b = 0; b < 3; ++b) {
           const float* in = x;
@@ -736,7 +750,7 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
         e.out0_dt = DT_F32;
         e.out1 = sx;
         e.out1_dt = ad;
-        DC_TRY(run_dense(h, h->ups[i], carry[cur], B, Lin, e, st));
+        DC_TRY(run_dense(h, h->ups[i], carry[cur], B, Lin, e, st, ad));
       }
       // ParralelBlock: mean of 3 ResBlock1 (convnext_utils.py:106-113,137-138)
       for (int b = 0; b < 3; ++b) {

@@ -35,7 +35,9 @@ void set_error(const char* fmt, ...);
     if (_r != DC_OK) return _r;                                                                \
   } while (0)
 
-enum { DT_F32 = 0, DT_BF16 = 1 };
+// DT_SPLIT: a (rows, 2C) bf16 tensor holding the two-term split [hi C | mid C] of fp32 values (4 bytes per value like fp32):
+// the operand format of the fp32 tensor-core kernel (gemm_f32x.cu), written directly by the producing epilogue
+enum { DT_F32 = 0, DT_BF16 = 1, DT_SPLIT = 2 };
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
 
 // ---------------------------------------------------------------- the one GEMM shape every dense layer maps to
@@ -70,6 +72,9 @@ struct Epilogue {
   float scale = 1.f;
   int out1_silu = 1;
   int prefetch = 1;  // L2-prefetch res / add1 / add2 of the next tile while waiting for its MMAs
+  // DT_SPLIT outputs: channels per LOGICAL row of the consumer's tensor (a ConvTranspose1d GEMM row holds `stride` output
+  // samples of split_seg = C_out channels each; 0 = ldo)
+  int split_seg = 0;
 };
 
 // Packed fp32 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, two IEEE fp32 operations per instruction, same rounding as

@@ -84,6 +84,22 @@ __device__ __forceinline__ void st4(void* base, size_t off, int dt, const float4
     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = pk;
   }
 }
+// four consecutive values of GEMM row `row`, columns n..n+3, as the two-term bf16 split [hi seg | mid seg] of the logical
+// row they belong to: logical rows have `seg` channels, a GEMM row holds ldo / seg of them (ConvTranspose1d phases)
+__device__ __forceinline__ void st4_split(void* base, size_t row, int n, int ldo, int seg, const float4 v) {
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 hi[4], mid[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    hi[k] = __float2bfloat16_rn(x[k]);
+    mid[k] = __float2bfloat16_rn(x[k] - __bfloat162float(hi[k]));
+  }
+  if (seg <= 0) seg = ldo;
+  const size_t lrow = row * (size_t)(ldo / seg) + (size_t)(n / seg);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(base) + lrow * (size_t)(2 * seg) + (n % seg);
+  *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
+  *reinterpret_cast<uint2*>(o + seg) = *reinterpret_cast<const uint2*>(mid);
+}
 __device__ __forceinline__ float4 ld4_nc(const void* base, size_t off, int dt) {  // read-only for the whole launch
   if (dt == DT_F32) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off));
   const uint2 x = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + off));
@@ -109,12 +125,16 @@ __device__ __forceinline__ void epilogue4(const Epilogue& e, size_t row, int n, 
     v.x = (v.x + a.x + c.x) * e.scale; v.y = (v.y + a.y + c.y) * e.scale;
     v.z = (v.z + a.z + c.z) * e.scale; v.w = (v.w + a.w + c.w) * e.scale;
   }
-  if (e.out0) st4(e.out0, off, e.out0_dt, v);
+  if (e.out0) {
+    if (e.out0_dt == DT_SPLIT) st4_split(e.out0, row, n, e.ldo, e.split_seg, v);
+    else st4(e.out0, off, e.out0_dt, v);
+  }
   if (e.out1) {
     if (e.out1_silu) {
       v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w);
     }
-    st4(e.out1, off, e.out1_dt, v);
+    if (e.out1_dt == DT_SPLIT) st4_split(e.out1, row, n, e.ldo, e.split_seg, v);
+    else st4(e.out1, off, e.out1_dt, v);
   }
 }
 

@@ -511,13 +511,15 @@ int launch_gather_rows(const float* table, const int64_t* idx, int64_t nrows, in
 struct ConvPostW {
   float w[13 * 32];  // [tap][channel]
 };
-template <typename TIn>
+// SPLIT: the input is the (rows, 2 * 32) bf16 two-term split [hi | mid] of fp32 values (DT_SPLIT): value = hi + mid
+template <typename TIn, bool SPLIT = false>
 __global__ void __launch_bounds__(128) conv_post_tanh_kernel(const TIn* __restrict__ in, const ConvPostW W, float bias,
                                                              float* __restrict__ out, int L) {
   constexpr int C = 32, K = 13, TILE = 512, ROWS = TILE + 16;  // 12 halo rows + 4 padding (float4 alignment)
+  constexpr int PITCH = SPLIT ? 2 * C : C;                     // input elements per row
   extern __shared__ float sx[];                                // [C][ROWS]
   const int b = blockIdx.y, l0 = blockIdx.x * TILE;
-  const TIn* ib = in + (size_t)b * L * C;
+  const TIn* ib = in + (size_t)b * L * PITCH;
   // fill: lane = row, 8 channels per 16-byte load (bf16) / 4 per load (fp32); transposed store is conflict-free
   for (int r = threadIdx.x; r < ROWS; r += 128) {
     const int l = l0 + r - 6;
@@ -525,13 +527,15 @@ __global__ void __launch_bounds__(128) conv_post_tanh_kernel(const TIn* __restri
     if constexpr (sizeof(TIn) == 2) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (ok) v = __ldg(reinterpret_cast<const uint4*>(ib + (size_t)l * C) + g);
-        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        uint4 v = make_uint4(0u, 0u, 0u, 0u), m = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) v = __ldg(reinterpret_cast<const uint4*>(ib + (size_t)l * PITCH) + g);
+        if (SPLIT && ok) m = __ldg(reinterpret_cast<const uint4*>(ib + (size_t)l * PITCH + C) + g);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w}, w[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          sx[(g * 8 + 2 * k) * ROWS + r] = __uint_as_float(u[k] << 16);
-          sx[(g * 8 + 2 * k + 1) * ROWS + r] = __uint_as_float(u[k] & 0xffff0000u);
+          sx[(g * 8 + 2 * k) * ROWS + r] = __uint_as_float(u[k] << 16) + (SPLIT ? __uint_as_float(w[k] << 16) : 0.f);
+          sx[(g * 8 + 2 * k + 1) * ROWS + r] =
+              __uint_as_float(u[k] & 0xffff0000u) + (SPLIT ? __uint_as_float(w[k] & 0xffff0000u) : 0.f);
         }
       }
     } else {
@@ -584,11 +588,14 @@ int launch_conv_post_tanh(const void* in, int in_dt, const float* w_host /*[13][
   if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
     DC_CUDA(cudaFuncSetAttribute(conv_post_tanh_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     DC_CUDA(cudaFuncSetAttribute(conv_post_tanh_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    DC_CUDA(cudaFuncSetAttribute(conv_post_tanh_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
   }
   dim3 grid((L + 511) / 512, B);
-  ProfScope ps(PC_CONV_POST, 2.0 * B * (double)L * 32 * 13, (double)B * L * (32.0 * (in_dt == DT_F32 ? 4 : 2) + 4.0), st);
-  if (in_dt == DT_F32) conv_post_tanh_kernel<float><<<grid, 128, SMEM, st>>>((const float*)in, W, bias, out, L);
+  ProfScope ps(PC_CONV_POST, 2.0 * B * (double)L * 32 * 13, (double)B * L * (32.0 * (in_dt == DT_BF16 ? 2 : 4) + 4.0), st);
+  if (in_dt == DT_SPLIT)
+    conv_post_tanh_kernel<__nv_bfloat16, true><<<grid, 128, SMEM, st>>>((const __nv_bfloat16*)in, W, bias, out, L);
+  else if (in_dt == DT_F32) conv_post_tanh_kernel<float><<<grid, 128, SMEM, st>>>((const float*)in, W, bias, out, L);
   else conv_post_tanh_kernel<__nv_bfloat16><<<grid, 128, SMEM, st>>>((const __nv_bfloat16*)in, W, bias, out, L);
   ++g_launches_pw;
   DC_CUDA(cudaGetLastError());
