@@ -550,7 +550,9 @@ __global__ void __launch_bounds__(128) conv_post_tanh_kernel(const TIn* __restri
   }
   __syncthreads();
   const int r0 = threadIdx.x * 4;  // this thread's outputs l0 + r0 .. + 3 need tile rows r0 .. r0 + 15
-  float acc[4] = {bias, bias, bias, bias};
+  // packed fp32 FMAs (two outputs per instruction, same IEEE results as scalar FMAs): outputs (0,1) and (2,3) of tap j
+  // read the row pairs (x[j], x[j+1]) and (x[j+2], x[j+3]); the pairs are formed once per channel for both parities
+  float2 a01 = make_float2(bias, bias), a23 = make_float2(bias, bias);
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     float x[16];
@@ -563,10 +565,12 @@ __global__ void __launch_bounds__(128) conv_post_tanh_kernel(const TIn* __restri
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       const float wj = W.w[j * C + c];
-#pragma unroll
-      for (int o = 0; o < 4; ++o) acc[o] = fmaf(x[o + j], wj, acc[o]);
+      const float2 w2 = make_float2(wj, wj);
+      a01 = ffma2(make_float2(x[j], x[j + 1]), w2, a01);
+      a23 = ffma2(make_float2(x[j + 2], x[j + 3]), w2, a23);
     }
   }
+  const float acc[4] = {a01.x, a01.y, a23.x, a23.y};
   const int l = l0 + r0;
   float* ob = out + (size_t)b * L;
   if (l + 3 < L) {

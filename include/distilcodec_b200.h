@@ -42,7 +42,8 @@ typedef enum {
 
 /* numeric mode: what `enable_bfloat16` selects in the reference API (distil_codec.py:545,550,581,590) */
 typedef enum {
-  DC_MODE_FP32 = 0, /* CUDA-core fp32 kernels; parity target 1e-4                                  */
+  DC_MODE_FP32 = 0, /* fp32-accurate: tensor cores on split-bf16 operands with chunked fp32 accumulation
+                       (option "fp32_tc", default) or CUDA-core fp32 kernels; parity target 1e-4          */
   DC_MODE_BF16 = 1  /* tcgen05 tensor-core kernels, bf16 operands / fp32 accumulate; target 1e-2   */
 } dc_mode;
 
