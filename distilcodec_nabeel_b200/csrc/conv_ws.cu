@@ -204,6 +204,9 @@ constexpr int kPairE1Warps = 4, kPairE2Warps = 16;
 #ifndef DC_PAIR_NG2
 #define DC_PAIR_NG2 4
 #endif
+#ifndef DC_PAIR_CW32
+#define DC_PAIR_CW32 1
+#endif
 constexpr int kPairNG2 = DC_PAIR_NG2, kPairG2Warps = kPairE2Warps / kPairNG2;
 static_assert(kPairNG2 == 2 || kPairNG2 == 4, "2 groups of 8 warps or 4 groups of 4");
 #ifdef DC_PAIR_TRACE  // experiment builds: per-role clock64 stamps of CTA 0, tiles 64..127 of its sequence
@@ -464,9 +467,11 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::mbar_wait_sleepy(&d2full[group], ph2);
       if (wg == 2 && lane == 0) PTRACE(12, i);
       ptx::tc_fence_after();
-      epilogue_tile<C, 16>(ep, variant, stg, tm_d2 + group * C, clip, o0, 0, T, wg, lane, o0 + MO);
+      // C = 64: whole 128-byte lines per access through a 16-row staging tile (same 2 KB per warp as 32 x 16)
+      constexpr int ECW = (C == 64 && DC_PAIR_CW32) ? 32 : 16, ESR = ECW == 32 ? 16 : 32;
+      epilogue_tile<C, ECW, ESR>(ep, variant, stg, tm_d2 + group * C, clip, o0, 0, T, wg, lane, o0 + MO);
       if constexpr (kPairG2Warps == 4)          // 4-warp groups: the same warp also takes the other column half
-        epilogue_tile<C, 16>(ep, variant, stg, tm_d2 + group * C, clip, o0, 0, T, wg + 4, lane, o0 + MO);
+        epilogue_tile<C, ECW, ESR>(ep, variant, stg, tm_d2 + group * C, clip, o0, 0, T, wg + 4, lane, o0 + MO);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&d2empty[group]);

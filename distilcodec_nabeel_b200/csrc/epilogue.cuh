@@ -17,16 +17,39 @@ __device__ __forceinline__ float silu_fast(float x) {  // x * sigmoid(x): 2 MUFU
   return x * r;
 }
 // two elements per call with packed fp32 arithmetic (FMUL2 / FADD2; bit-identical to the scalar form): the epilogue
-// warps are issue-bound, so 3 packed + 4 MUFU instructions per pair instead of 10 matter
+// warps are issue-bound, so 3 packed + 4 MUFU instructions per pair instead of 10 matter.
+// DC_SILU_NR=1 (A/B, rejected): reciprocal by integer seed + two packed Newton steps instead of MUFU.RCP (relative
+// error < 7e-6).  ncu shows the XU pipe at 65 % on the short-K launches run alone, but in the step the extra 6 issue
+// slots per pair cost more than the MUFU results they save: 535 -> 550 ms per step, conv_ws_pairs 46.7 -> 58.5 ms,
+// no launch faster (profiles/r2_ncu_summary.md).
+#ifndef DC_SILU_NR
+#define DC_SILU_NR 0
+#endif
 __device__ __forceinline__ float2 silu_fast2(float2 x) {
-  const float2 t = fmul2(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
-  float2 e, r;
+  float2 t = fmul2(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  float2 e;
+#if DC_SILU_NR
+  t.x = fminf(t.x, 126.f);
+  t.y = fminf(t.y, 126.f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+  const float2 nd = ffma2(e, make_float2(-1.f, -1.f), make_float2(-1.f, -1.f));  // -(1 + e)
+  // 0x7EF311C7 - bits(d), with the sign bit of -d folded into the constant
+  float2 r = make_float2(__uint_as_float(0xFEF311C7u - __float_as_uint(nd.x)),
+                         __uint_as_float(0xFEF311C7u - __float_as_uint(nd.y)));
+  const float2 two = make_float2(2.f, 2.f);
+  r = fmul2(r, ffma2(nd, r, two));
+  r = fmul2(r, ffma2(nd, r, two));
+  return fmul2(x, r);
+#else
+  float2 r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
   const float2 d = fadd2(e, make_float2(1.f, 1.f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
   return fmul2(x, r);
+#endif
 }
 // exact-erf GELU (nn.GELU(), convnext_utils.py:254) in 12 instructions with ONE MUFU op:
 //   gelu(x) = max(x, 0) - a * Phi(-a),  a = |x|,  Phi(-a) = 0.5 erfc(a / sqrt 2) = 2^q(a)
@@ -170,10 +193,11 @@ __device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, const float4 v) {
 
 // One 32-row x CW-column chunk of one warp.  stg: the warp's XOR-swizzled transpose tile (already written);
 // off0: element offset (row * ldo + n) of this lane's first row group; nvalid: row groups of this lane with t < T.
-template <int V, int CW, bool LINEAR = false /* staging tile written un-swizzled (transposed accumulators) */>
+template <int V, int CW, bool LINEAR = false /* staging tile written un-swizzled (transposed accumulators) */,
+          int ROWS = 32 /* rows in the staging tile */>
 __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, const float* stg, int lane, size_t off0,
                                                int nvalid, const float4 b4, const float4 g4) {
-  constexpr int CPR = CW / 4, RPI = 32 / CPR, NG = 32 / RPI;
+  constexpr int CPR = CW / 4, RPI = 32 / CPR, NG = ROWS / RPI;
   constexpr bool kRes = V == EV_RES_F32_BF16S || V == EV_RES_F32 || V == EV_RES_MEAN_BF16S || V == EV_GAMMA_RES_F32;
   constexpr bool kOut0F = V == EV_RES_F32_BF16S || V == EV_RES_F32 || V == EV_F32_BF16S || V == EV_GAMMA_RES_F32 || V == EV_F32;
   constexpr bool kOut0B = V == EV_SILU_BF16 || V == EV_GELU_BF16 || V == EV_BF16;
@@ -233,10 +257,10 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, const float* 
 }
 
 // generic (runtime-flag) chunk
-template <int CW, bool LINEAR = false>
+template <int CW, bool LINEAR = false, int ROWS = 32>
 __device__ __forceinline__ void epilogue_chunk_generic(const Epilogue& ep, const float* stg, int lane, size_t off0,
                                                        int nvalid, int n, const float4 b4, const float4 g4) {
-  constexpr int CPR = CW / 4, RPI = 32 / CPR, NG = 32 / RPI;
+  constexpr int CPR = CW / 4, RPI = 32 / CPR, NG = ROWS / RPI;
   const int cg = lane % CPR, rsub = lane / CPR;
   const size_t stride = (size_t)RPI * ep.ldo;
   float4 r4[NG];
@@ -252,20 +276,20 @@ __device__ __forceinline__ void epilogue_chunk_generic(const Epilogue& ep, const
   }
 }
 
-template <int CW, bool LINEAR>
+template <int CW, bool LINEAR, int ROWS = 32>
 __device__ __forceinline__ void epilogue_dispatch(const Epilogue& ep, int variant, const float* stg, int lane,
                                                   size_t off0, int nvalid, int n, const float4 b4, const float4 g4) {
   switch (variant) {
-    case EV_SILU_BF16: epilogue_chunk<EV_SILU_BF16, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
-    case EV_RES_F32_BF16S: epilogue_chunk<EV_RES_F32_BF16S, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
-    case EV_RES_F32: epilogue_chunk<EV_RES_F32, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
-    case EV_RES_MEAN_BF16S: epilogue_chunk<EV_RES_MEAN_BF16S, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
-    case EV_F32_BF16S: epilogue_chunk<EV_F32_BF16S, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
-    case EV_GELU_BF16: epilogue_chunk<EV_GELU_BF16, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
-    case EV_GAMMA_RES_F32: epilogue_chunk<EV_GAMMA_RES_F32, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
-    case EV_F32: epilogue_chunk<EV_F32, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
-    case EV_BF16: epilogue_chunk<EV_BF16, CW, LINEAR>(ep, stg, lane, off0, nvalid, b4, g4); break;
-    default: epilogue_chunk_generic<CW, LINEAR>(ep, stg, lane, off0, nvalid, n, b4, g4); break;
+    case EV_SILU_BF16: epilogue_chunk<EV_SILU_BF16, CW, LINEAR, ROWS>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_RES_F32_BF16S: epilogue_chunk<EV_RES_F32_BF16S, CW, LINEAR, ROWS>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_RES_F32: epilogue_chunk<EV_RES_F32, CW, LINEAR, ROWS>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_RES_MEAN_BF16S: epilogue_chunk<EV_RES_MEAN_BF16S, CW, LINEAR, ROWS>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_F32_BF16S: epilogue_chunk<EV_F32_BF16S, CW, LINEAR, ROWS>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_GELU_BF16: epilogue_chunk<EV_GELU_BF16, CW, LINEAR, ROWS>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_GAMMA_RES_F32: epilogue_chunk<EV_GAMMA_RES_F32, CW, LINEAR, ROWS>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_F32: epilogue_chunk<EV_F32, CW, LINEAR, ROWS>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    case EV_BF16: epilogue_chunk<EV_BF16, CW, LINEAR, ROWS>(ep, stg, lane, off0, nvalid, b4, g4); break;
+    default: epilogue_chunk_generic<CW, LINEAR, ROWS>(ep, stg, lane, off0, nvalid, n, b4, g4); break;
   }
 }
 
@@ -292,10 +316,15 @@ __device__ __forceinline__ void epilogue_prefetch(const Epilogue& ep, int clip, 
 // One 128 x BN output tile: the 8 epilogue warps (CTA warps 2..9) each take a TMEM lane quarter (rows) and one half of
 // the columns.  TMEM -> registers (thread = row) -> XOR-swizzled per-warp smem tile -> (lane = 4 columns) -> global.
 // tmem_acc: TMEM address (lane 0) of the tile's accumulator; stg: this warp's 32 x CW fp32 transpose buffer.
-template <int BN, int CW = (BN >= 64 ? 32 : 16) /* chunk width in columns */>
+// SROWS = 16: the staging tile holds 16 rows only (half the shared memory at the same chunk width): the two lane
+// halves of the warp stage and store their rows one after the other.  conv_ws_pair<64> has 2 KB of staging per warp;
+// with 16-column chunks every global access of its epilogue touched half a 128-byte line and the L1 data pipe ran at
+// 82-86 % of its wavefront peak at 1.75 GHz (profiles/r2_ncu_summary.md), i.e. saturated at the in-step clock.
+template <int BN, int CW = (BN >= 64 ? 32 : 16) /* chunk width in columns */, int SROWS = 32>
 __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int variant, float* stg, uint32_t tmem_acc, int clip,
                                               int t0, int n0, int T, int warp, int lane, int t_lim = 0x7fffffff) {
   // t_lim: rows t >= min(T, t_lim) are not stored (tiles whose last accumulator rows are not valid outputs)
+  static_assert(SROWS == 32 || SROWS == 16, "staging rows");
   constexpr int CPR = CW / 4;             // 16-byte column groups per row (8 or 4)
   constexpr int RPI = 32 / CPR;           // rows covered by one warp-wide access (4 or 8)
   const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -304,26 +333,52 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int variant, f
 #pragma unroll 1
   for (int c = 0; c < (BN / 2) / CW; ++c) {
     const int col0 = half * (BN / 2) + c * CW;  // first column of this chunk within the tile
-    uint32_t acc[CW];
-    if constexpr (CW == 32) ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, acc);
-    else ptx::tmem_ld_32x16(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, acc);
     // column parameters of this lane's 4 columns (independent of the row)
     const int n = n0 + col0 + cg * 4;
     const float4 b4 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 g4 = ep.gamma ? __ldg(reinterpret_cast<const float4*>(ep.gamma + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
-    ptx::tmem_ld_wait();
     // thread = row `lane`: 16-byte group i goes to slot (i ^ swz(lane)); conflict-free for both access phases
     const int wswz = CW == 32 ? (lane & 7) : ((lane >> 1) & 3);
+    if constexpr (SROWS == 32) {
+      uint32_t acc[CW];
+      if constexpr (CW == 32) ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, acc);
+      else ptx::tmem_ld_32x16(tmem_acc + ((uint32_t)(q * 32) << 16) + col0, acc);
+      ptx::tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < CPR; ++i)
-      *reinterpret_cast<uint4*>(stg + lane * CW + ((i ^ wswz) << 2)) =
-          make_uint4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
-    __syncwarp();
-    const int tb = t0 + q * 32 + rsub;  // first row of this lane
-    const int nvalid = min(32 / RPI, max(0, (min(T, t_lim) - tb + RPI - 1) / RPI));
-    const size_t off0 = ((size_t)clip * T + tb) * (size_t)ep.ldo + n;
-    epilogue_dispatch<CW, false>(ep, variant, stg, lane, off0, nvalid, n, b4, g4);
-    __syncwarp();
+      for (int i = 0; i < CPR; ++i)
+        *reinterpret_cast<uint4*>(stg + lane * CW + ((i ^ wswz) << 2)) =
+            make_uint4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+      __syncwarp();
+      const int tb = t0 + q * 32 + rsub;  // first row of this lane
+      const int nvalid = min(32 / RPI, max(0, (min(T, t_lim) - tb + RPI - 1) / RPI));
+      const size_t off0 = ((size_t)clip * T + tb) * (size_t)ep.ldo + n;
+      epilogue_dispatch<CW, false, 32>(ep, variant, stg, lane, off0, nvalid, n, b4, g4);
+      __syncwarp();
+    } else {
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        // TMEM loads are warp-wide: both lane halves read their rows in either pass (16 columns at a time, so that
+        // no more than 16 accumulator registers are live), the half whose rows this pass stages writes them
+#pragma unroll
+        for (int hc = 0; hc < CW / 16; ++hc) {
+          uint32_t acc[16];
+          ptx::tmem_ld_32x16(tmem_acc + ((uint32_t)(q * 32) << 16) + col0 + hc * 16, acc);
+          ptx::tmem_ld_wait();
+          if ((lane >> 4) == pass) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(stg + (lane & 15) * CW + (((hc * 4 + i) ^ wswz) << 2)) =
+                  make_uint4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+          }
+        }
+        __syncwarp();
+        const int tb = t0 + q * 32 + pass * 16 + rsub;
+        const int nvalid = min(16 / RPI, max(0, (min(T, t_lim) - tb + RPI - 1) / RPI));
+        const size_t off0 = ((size_t)clip * T + tb) * (size_t)ep.ldo + n;
+        epilogue_dispatch<CW, false, 16>(ep, variant, stg, lane, off0, nvalid, n, b4, g4);
+        __syncwarp();
+      }
+    }
   }
 }
 // ---------------------------------------------------------------- direct epilogue for TRANSPOSED accumulators
