@@ -66,6 +66,15 @@ int launch_split_f32(const float* in, __nv_bfloat16* out, size_t rows, int C, cu
 }
 
 // ---------------------------------------------------------------- the kernel
+#ifndef DC_F32X_OCC
+#define DC_F32X_OCC 2
+#endif
+#ifndef DC_F32X_PREFETCH
+#define DC_F32X_PREFETCH 1
+#endif
+#ifndef DC_F32X_NARROW_BK32   // N <= 64 layers with C % 64 == 0 on the BK = 32 configuration (two CTAs per SM)
+#define DC_F32X_NARROW_BK32 1
+#endif
 namespace f32x {
 constexpr int kChunkStages = 4;   // pipeline stages (of BK = 64: K = 256 per term) per partial accumulation chain
 constexpr int kStages = 3;
@@ -85,6 +94,10 @@ struct Smem {
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "swizzled tiles need 1024-byte aligned bases");
   static_assert(TOTAL <= 232448, "shared memory budget");
+  // narrow tiles (N <= 64, BK = 32) fit twice per SM: their per-tile chain TMA -> MMA chunks -> adds -> epilogue with
+  // its DRAM round trips is latency-bound with one CTA per SM (one T accumulator: the epilogue of tile i and the adds
+  // of tile i + 1 are the same warps)
+  static constexpr int CTAS_PER_SM = (DC_F32X_OCC >= 2 && 2 * (TOTAL + 1024) <= 233472) ? 2 : 1;
 };
 }  // namespace f32x
 
@@ -107,7 +120,7 @@ __device__ __forceinline__ uint32_t f32x_zero_taps(const ConvGemmShape& s, int n
 }
 
 template <int BN, int BK>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(320, f32x::Smem<BN, BK>::CTAS_PER_SM)
 gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvGemmShape s,
                  Epilogue ep, int variant, int tiles_per_clip, int m_tiles, int n_tiles) {
   using namespace f32x;
@@ -316,7 +329,8 @@ static int launch_f32x_cfg(const __nv_bfloat16* A2, const __nv_bfloat16* W2, con
     DC_TRY(make_tmap_bf16(&tmW, W2, 2, dims, strides, box, BK * 2));
   }
   const long long total = m_tiles * n_tiles;
-  const int grid = (int)(total < sm_count ? total : sm_count);
+  const long long slots = (long long)sm_count * L::CTAS_PER_SM;
+  const int grid = (int)(total < slots ? total : slots);
   {
     const double rows = (double)s.B * s.T;
     const double macs = rows * s.N * s.J * s.C * s.alg_scale;
@@ -326,7 +340,7 @@ static int launch_f32x_cfg(const __nv_bfloat16* A2, const __nv_bfloat16* W2, con
     ProfScope ps(PC_GEMM_F32, 2.0 * macs, rows * s.C * 4.0 + (double)s.N * s.J * s.C * 4.0 + rows * s.N * out_bytes, st,
                  "x<%d,%d>|C%d N%d J%d d%d e%d", BN, BK, s.C, s.N, s.J, s.dil, esig);
     Epilogue eg = e;
-    eg.prefetch = 0;
+    eg.prefetch = DC_F32X_PREFETCH ? e.prefetch : 0;
     gemm_f32x_kernel<BN, BK><<<grid, 320, L::TOTAL, st>>>(tmA, tmW, s, eg, epilogue_variant(e), tiles_per_clip, (int)m_tiles,
                                                          n_tiles);
   }
@@ -346,7 +360,7 @@ int launch_gemm_f32x(const __nv_bfloat16* A2, const __nv_bfloat16* W2, const Con
     s.T = s.B * s.T;
     s.B = 1;
   }
-  if (s.C % 64 == 0) {
+  if (s.C % 64 == 0 && !(DC_F32X_NARROW_BK32 && s.N % 128 != 0)) {
     if (s.N % 128 == 0) return launch_f32x_cfg<128, 64>(A2, W2, s, e, st, sm_count);
     if (s.N % 64 == 0) return launch_f32x_cfg<64, 64>(A2, W2, s, e, st, sm_count);
     return launch_f32x_cfg<32, 64>(A2, W2, s, e, st, sm_count);
