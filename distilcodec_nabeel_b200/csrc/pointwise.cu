@@ -505,79 +505,102 @@ int launch_gather_rows(const float* table, const int64_t* idx, int64_t nrows, in
 
 // ------------------------------------------------------------------------------------------ conv_post + tanh
 // Conv1d(32 -> 1, k13, pad 6) + tanh (models/generators.py:141-145) on the already SiLU'd channels-last input.
-// 416 FMAs per output sample and a single output channel: CUDA-core work.  Each thread produces 4 consecutive
-// samples, so per input channel it needs 16 consecutive rows (four conflict-free LDS.128 from a channel-major
-// shared-memory tile) for 52 FMAs whose weight operand comes straight from the kernel-parameter constant bank.
+// 416 FMAs per output sample and a single output channel: CUDA-core work, and bound by instruction issue, not by HBM
+// (round 2: 2.33 ms per step at 0.27 of the copy bandwidth with one FMA pair per (tap, 2 samples): the packed operands
+// (x[j], x[j+1]) and (w, w) had to be formed with moves, 72 instructions per channel and 4 samples).
+// Now the two lanes of a packed FMA are two CHANNELS: the shared-memory tile holds (channel pair) float2 elements, a
+// weight pair is one 64-bit constant-bank operand, and a thread keeps 8 consecutive samples x 2 partial sums: per channel
+// pair 20 LDS.64 + 104 FFMA2, i.e. 15.5 instructions per channel and 4 samples.  Tile layout [pair][row % 8][row / 8]:
+// the fill (lane = row) and the compute reads (lane = 8-row group) are both conflict-free.
 struct ConvPostW {
   float w[13 * 32];  // [tap][channel]
 };
 // SPLIT: the input is the (rows, 2 * 32) bf16 two-term split [hi | mid] of fp32 values (DT_SPLIT): value = hi + mid
 template <typename TIn, bool SPLIT = false>
 __global__ void __launch_bounds__(128) conv_post_tanh_kernel(const TIn* __restrict__ in, const ConvPostW W, float bias,
-                                                             float* __restrict__ out, int L) {
-  constexpr int C = 32, K = 13, TILE = 512, ROWS = TILE + 16;  // 12 halo rows + 4 padding (float4 alignment)
-  constexpr int PITCH = SPLIT ? 2 * C : C;                     // input elements per row
-  extern __shared__ float sx[];                                // [C][ROWS]
+                                                            float* __restrict__ out, int L) {
+  constexpr int C = 32, K = 13, TILE = 512, ROWS = TILE + 16;   // 12 halo rows + 4 padding
+  // R8 = 5 (mod 16) and PL = 1 (mod 4): the fill's 64-bit stores (half-warp = 4 rows x 4 column groups of one
+  // coalesced 512-byte global access) land in 16 distinct bank pairs
+  constexpr int R8 = 69, PL = 8 * R8 + 1;
+  static_assert(R8 >= ROWS / 8 && R8 % 16 == 5 && PL % 4 == 1, "tile pitches");
+  constexpr int PITCH = SPLIT ? 2 * C : C;                      // input elements per row
+  extern __shared__ float2 sx2[];                               // [C / 2][PL]: pair plane, element (row % 8) * R8 + row / 8
   const int b = blockIdx.y, l0 = blockIdx.x * TILE;
   const TIn* ib = in + (size_t)b * L * PITCH;
-  // fill: lane = row, 8 channels per 16-byte load (bf16) / 4 per load (fp32); transposed store is conflict-free
-  for (int r = threadIdx.x; r < ROWS; r += 128) {
-    const int l = l0 + r - 6;
-    const bool ok = l >= 0 && l < L;
-    if constexpr (sizeof(TIn) == 2) {
+  // fill: every global access of a warp is one contiguous run of whole rows (lane = (row, 16-byte group)); with lane =
+  // row each 128-byte line was touched by 4 separate instructions and, with 3 x 68 KB of the SM's L1 carved out as
+  // shared memory, re-fetched from L2: the kernel was bound by that, not by its FMAs (2.3 ms before and after the
+  // instruction count was halved)
+  if constexpr (sizeof(TIn) == 2) {
+    const int g = threadIdx.x & 3;
+#pragma unroll 4
+    for (int r = threadIdx.x >> 2; r < ROWS; r += 32) {
+      const int l = l0 + r - 6;
+      const bool ok = l >= 0 && l < L;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u), m = make_uint4(0u, 0u, 0u, 0u);
+      if (ok) v = __ldg(reinterpret_cast<const uint4*>(ib + (size_t)l * PITCH) + g);
+      if (SPLIT && ok) m = __ldg(reinterpret_cast<const uint4*>(ib + (size_t)l * PITCH + C) + g);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w}, w[4] = {m.x, m.y, m.z, m.w};
+      float2* dst = sx2 + (g * 4) * PL + (r & 7) * R8 + (r >> 3);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 v = make_uint4(0u, 0u, 0u, 0u), m = make_uint4(0u, 0u, 0u, 0u);
-        if (ok) v = __ldg(reinterpret_cast<const uint4*>(ib + (size_t)l * PITCH) + g);
-        if (SPLIT && ok) m = __ldg(reinterpret_cast<const uint4*>(ib + (size_t)l * PITCH + C) + g);
-        const uint32_t u[4] = {v.x, v.y, v.z, v.w}, w[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          sx[(g * 8 + 2 * k) * ROWS + r] = __uint_as_float(u[k] << 16) + (SPLIT ? __uint_as_float(w[k] << 16) : 0.f);
-          sx[(g * 8 + 2 * k + 1) * ROWS + r] =
-              __uint_as_float(u[k] & 0xffff0000u) + (SPLIT ? __uint_as_float(w[k] & 0xffff0000u) : 0.f);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) v = __ldg(reinterpret_cast<const float4*>(ib + (size_t)l * C) + g);
-        sx[(g * 4 + 0) * ROWS + r] = v.x; sx[(g * 4 + 1) * ROWS + r] = v.y;
-        sx[(g * 4 + 2) * ROWS + r] = v.z; sx[(g * 4 + 3) * ROWS + r] = v.w;
-      }
+      for (int k = 0; k < 4; ++k)
+        dst[k * PL] = make_float2(__uint_as_float(u[k] << 16) + (SPLIT ? __uint_as_float(w[k] << 16) : 0.f),
+                                  __uint_as_float(u[k] & 0xffff0000u) + (SPLIT ? __uint_as_float(w[k] & 0xffff0000u) : 0.f));
+    }
+  } else {
+    const int g = threadIdx.x & 7;
+#pragma unroll 4
+    for (int r = threadIdx.x >> 3; r < ROWS; r += 16) {
+      const int l = l0 + r - 6;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (l >= 0 && l < L) v = __ldg(reinterpret_cast<const float4*>(ib + (size_t)l * C) + g);
+      float2* dst = sx2 + (g * 2) * PL + (r & 7) * R8 + (r >> 3);
+      dst[0] = make_float2(v.x, v.y);
+      dst[PL] = make_float2(v.z, v.w);
     }
   }
   __syncthreads();
-  const int r0 = threadIdx.x * 4;  // this thread's outputs l0 + r0 .. + 3 need tile rows r0 .. r0 + 15
-  // packed fp32 FMAs (two outputs per instruction, same IEEE results as scalar FMAs): outputs (0,1) and (2,3) of tap j
-  // read the row pairs (x[j], x[j+1]) and (x[j+2], x[j+3]); the pairs are formed once per channel for both parities
-  float2 a01 = make_float2(bias, bias), a23 = make_float2(bias, bias);
+  // thread (t, h): samples l0 + 8 t .. + 7 over the channel pairs [8 h, 8 h + 8); they need tile rows 8 t .. 8 t + 19 =
+  // (row % 8, row / 8) = (k & 7, t + (k >> 3)).  The two halves are added through shared memory (12 warps per SM
+  // instead of 6: with 64-thread blocks the LDS -> FFMA2 latency was exposed and the kernel ran at 3.1 ms).
+  const int t = threadIdx.x & 63, h = threadIdx.x >> 6;
+  float2 acc[8];
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    float x[16];
-    const float4* p = reinterpret_cast<const float4*>(sx + c * ROWS + r0);
+  for (int o = 0; o < 8; ++o) acc[o] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 v = p[i];
-      x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
-    }
+  for (int ci = 0; ci < C / 4; ++ci) {
+    float2 x[20];
+#pragma unroll
+    for (int k = 0; k < 20; ++k) x[k] = sx2[(h * (C / 4) + ci) * PL + (k & 7) * R8 + t + (k >> 3)];
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-      const float wj = W.w[j * C + c];
-      const float2 w2 = make_float2(wj, wj);
-      a01 = ffma2(make_float2(x[j], x[j + 1]), w2, a01);
-      a23 = ffma2(make_float2(x[j + 2], x[j + 3]), w2, a23);
+      // warp-uniform h: both candidates are constant-bank operands
+      const float2 w2 = h ? make_float2(W.w[j * C + C / 2 + 2 * ci], W.w[j * C + C / 2 + 2 * ci + 1])
+                          : make_float2(W.w[j * C + 2 * ci], W.w[j * C + 2 * ci + 1]);
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = ffma2(x[o + j], w2, acc[o]);
     }
   }
-  const float acc[4] = {a01.x, a01.y, a23.x, a23.y};
-  const int l = l0 + r0;
+  __syncthreads();                                   // the tile is dead: reuse its first 2 KB for the partial sums
+  float* red = reinterpret_cast<float*>(sx2);        // [8][64]
+  if (h == 1) {
+#pragma unroll
+    for (int o = 0; o < 8; ++o) red[o * 64 + t] = acc[o].x + acc[o].y;
+  }
+  __syncthreads();
+  if (h == 1) return;
+  const int l = l0 + t * 8;
   float* ob = out + (size_t)b * L;
-  if (l + 3 < L) {
-    *reinterpret_cast<float4*>(ob + l) = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
+  float y[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) y[o] = tanhf((acc[o].x + acc[o].y) + red[o * 64 + t] + bias);
+  if (l + 7 < L) {
+    *reinterpret_cast<float4*>(ob + l) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(ob + l + 4) = make_float4(y[4], y[5], y[6], y[7]);
   } else {
-    for (int o = 0; o < 4; ++o)
-      if (l + o < L) ob[l + o] = tanhf(acc[o]);
+    for (int o = 0; o < 8; ++o)
+      if (l + o < L) ob[l + o] = y[o];
   }
 }
 int launch_conv_post_tanh(const void* in, int in_dt, const float* w_host /*[13][32], host*/, float bias, float* out,
@@ -585,7 +608,7 @@ int launch_conv_post_tanh(const void* in, int in_dt, const float* w_host /*[13][
   DC_CHECK(L % 4 == 0, DC_ERR_SHAPE, "conv_post: output length must be a multiple of 4");
   ConvPostW W;
   memcpy(W.w, w_host, sizeof(W.w));
-  constexpr int SMEM = 32 * (512 + 16) * 4;
+  constexpr int SMEM = 16 * (8 * 69 + 1) * 8;  // [C / 2][PL] float2, see the kernel
   static std::atomic<unsigned> attr_dev_mask{0u};  // once per (function, device); atomic because host threads driving different devices meet here
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));

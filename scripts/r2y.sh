@@ -1,15 +1,19 @@
-AB=${AB:-mufu}
-timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_e2e.py tests/test_gpu_config_size.py -m gpu -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_modules.py tests/test_gpu_dropin_joined.py -m gpu -x -q 2>&1 | tail -3
 for i in 1 2; do
-  for lib in $AB new; do
-    if [ $lib = new ]; then unset DC_LIB; else export DC_LIB=$PWD/ab/libdc_$AB.so; fi
-    timeout 600 python bench.py --steps 6 --warmup 3 --detail-out gpurun_out/r2y_detail_${lib}_$i.json > gpurun_out/r2y_${lib}_$i.json 2> gpurun_out/r2y_${lib}_$i.err
+    timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --detail-out gpurun_out/r2y_detail_new_$i.json > gpurun_out/r2y_new_$i.json 2> gpurun_out/r2y_new_$i.err
     python - <<PY
 import json
-l=json.loads(open('gpurun_out/r2y_${lib}_$i.json').read().strip().splitlines()[-1])
-d=json.load(open('gpurun_out/r2y_detail_${lib}_$i.json'))
+l=json.loads(open('gpurun_out/r2y_new_$i.json').read().strip().splitlines()[-1])
+d=json.load(open('gpurun_out/r2y_detail_new_$i.json'))
 k={x['name']:x['ms_per_step'] for x in d['kernels']}
-print('$lib $i', round(l['ms_per_step'],1), l['clocks']['sm_mhz'], ' '.join(f"{n}={v:.1f}" for n,v in k.items() if v>5))
+print('new $i', round(l['ms_per_step'],1), l['clocks']['sm_mhz'], ' '.join(f"{n}={v:.2f}" for n,v in k.items() if v>0.3))
 PY
-  done
 done
+timeout 600 python bench.py --mode fp32 --clips 64 --steps 4 --warmup 3 --no-cpu-baseline --detail-out gpurun_out/r2y_detail_fp32.json > gpurun_out/r2y_fp32.json 2> gpurun_out/r2y_fp32.err
+python - <<PY
+import json
+l=json.loads(open('gpurun_out/r2y_fp32.json').read().strip().splitlines()[-1])
+d=json.load(open('gpurun_out/r2y_detail_fp32.json'))
+k={x['name']:x['ms_per_step'] for x in d['kernels']}
+print('fp32', round(l['ms_per_step'],1), round(l['value'],1), ' '.join(f"{n}={v:.2f}" for n,v in k.items() if v>0.3))
+PY
