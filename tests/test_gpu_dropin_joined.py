@@ -100,3 +100,21 @@ def test_decode_from_codes_batch_decodes_every_clip(codecs):
             y_ref = ref.decode_from_codes(padded, minus_token_offset=False, enable_bfloat16=False)
             assert tuple(outs[i].shape) == tuple(y_ref.shape) == (1, 1, 256 * max(lens))
             assert rel_err(outs[i].float(), y_ref.float()) < 1e-4, i
+
+
+def test_bf16_encoder_error_on_the_stress_weights_is_the_precision_floor(codecs):
+    """tests/test_gpu_e2e.py gates the W1 encoder at 2e-2 in bf16 mode (1e-2 is defined on W0).  The reason is the
+    precision, not this implementation: the reference's OWN encoder under its own bf16 autocast (distil_codec.py:560-563)
+    on the same GPU is as far from its fp32 result.  Gate: this path's error stays within 1.25x of the reference's."""
+    ref, patched = codecs
+    mel = torch.from_numpy(golden("e2e_W1.npz")["mel"]).to(ref.device)
+    with torch.no_grad():
+        y32 = ref.encoder(mel).float()
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+            y_ref16 = ref.encoder(mel).float()
+            y_b200 = patched.encoder(mel).float()
+    assert patched.encoder._engines.get("bf16").launch_count() > 0
+    e_ref, e_b200 = rel_err(y_ref16, y32), rel_err(y_b200, y32)
+    print(f"W1 encoder, bf16: reference autocast {e_ref:.3e}, this path {e_b200:.3e}")
+    assert e_ref > 2e-3                       # the stress weights do expose the bf16 rounding
+    assert e_b200 < max(1e-2, 1.25 * e_ref), (e_b200, e_ref)
