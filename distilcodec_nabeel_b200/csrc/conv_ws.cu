@@ -467,11 +467,19 @@ conv_ws_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::mbar_wait_sleepy(&d2full[group], ph2);
       if (wg == 2 && lane == 0) PTRACE(12, i);
       ptx::tc_fence_after();
-      // C = 64: whole 128-byte lines per access through a 16-row staging tile (same 2 KB per warp as 32 x 16)
-      constexpr int ECW = (C == 64 && DC_PAIR_CW32) ? 32 : 16, ESR = ECW == 32 ? 16 : 32;
-      epilogue_tile<C, ECW, ESR>(ep, variant, stg, tm_d2 + group * C, clip, o0, 0, T, wg, lane, o0 + MO);
-      if constexpr (kPairG2Warps == 4)          // 4-warp groups: the same warp also takes the other column half
-        epilogue_tile<C, ECW, ESR>(ep, variant, stg, tm_d2 + group * C, clip, o0, 0, T, wg + 4, lane, o0 + MO);
+      // whole 128-byte lines per access through a 16-row staging tile (same 2 KB per warp as 32 rows x 16 columns)
+      if constexpr (DC_PAIR_CW32 && C == 64) {
+        epilogue_tile<C, 32, 16>(ep, variant, stg, tm_d2 + group * C, clip, o0, 0, T, wg, lane, o0 + MO);
+        if constexpr (kPairG2Warps == 4)        // 4-warp groups: the same warp also takes the other column half
+          epilogue_tile<C, 32, 16>(ep, variant, stg, tm_d2 + group * C, clip, o0, 0, T, wg + 4, lane, o0 + MO);
+      } else if constexpr (DC_PAIR_CW32 && C == 32 && kPairG2Warps == 4) {
+        // all 32 columns are one chunk: "column half 0" of a 64-wide tile
+        epilogue_tile<2 * C, 32, 16>(ep, variant, stg, tm_d2 + group * C, clip, o0, 0, T, wg, lane, o0 + MO);
+      } else {
+        epilogue_tile<C, 16>(ep, variant, stg, tm_d2 + group * C, clip, o0, 0, T, wg, lane, o0 + MO);
+        if constexpr (kPairG2Warps == 4)
+          epilogue_tile<C, 16>(ep, variant, stg, tm_d2 + group * C, clip, o0, 0, T, wg + 4, lane, o0 + MO);
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&d2empty[group]);
