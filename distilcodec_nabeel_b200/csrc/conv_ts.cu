@@ -510,7 +510,8 @@ static int launch_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const Conv
     Epilogue eg = e;
     // L2-prefetching the residual tile while the MMAs run pays only where the layer is HBM-latency-bound (A/B on one
     // box: k = 3 at C = 256 -6 % / -11 %; k = 7 +9 %; the tensor-bound k = 11 layers lose ~3 %)
-    eg.prefetch = (s.J * s.C <= 768) ? e.prefetch : 0;
+    // option epi_prefetch: 1 = that rule, 2 = also k = 7 at C = 256, 3 = every layer, 0 = never
+    eg.prefetch = (e.prefetch >= 3 || (e.prefetch == 2 && s.J * s.C <= 1792) || (e.prefetch == 1 && s.J * s.C <= 768)) ? 1 : 0;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);

@@ -72,6 +72,9 @@ int launch_split_f32(const float* in, __nv_bfloat16* out, size_t rows, int C, cu
 #ifndef DC_F32X_PREFETCH
 #define DC_F32X_PREFETCH 1
 #endif
+#ifndef DC_F32X_WS            // weights-stationary kernel for the C = N = 32 / 64 layers
+#define DC_F32X_WS 1
+#endif
 #ifndef DC_F32X_NARROW_BK32   // N <= 64 layers with C % 64 == 0 on the BK = 32 configuration (two CTAs per SM)
 #define DC_F32X_NARROW_BK32 1
 #endif
@@ -113,6 +116,43 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// T[rows of this warp, its column half] (+)= P, 32 columns at a time (16 for the narrowest tiles); tT / tP already
+// carry the warp's TMEM lane offset
+template <int BN>
+__device__ __forceinline__ void f32x_add_partial(uint32_t tT, uint32_t tP, int half, bool first) {
+  constexpr int PIECE = (BN / 2) >= 32 ? 32 : 16;
+#pragma unroll 1
+  for (int c = 0; c < (BN / 2) / PIECE; ++c) {
+    const uint32_t col = half * (BN / 2) + c * PIECE;
+    if constexpr (PIECE == 32) {
+      uint32_t p[32], t[32];
+      ptx::tmem_ld_32x32(tP + col, p);
+      if (!first) ptx::tmem_ld_32x32(tT + col, t);
+      ptx::tmem_ld_wait();
+      if (!first) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p[i] = __float_as_uint(__fadd_rn(__uint_as_float(t[i]), __uint_as_float(p[i])));
+      }
+      tmem_st_32x32(tT + col, p);
+    } else {
+      uint32_t p[16], t[16];
+      ptx::tmem_ld_32x16(tP + col, p);
+      if (!first) ptx::tmem_ld_32x16(tT + col, t);
+      ptx::tmem_ld_wait();
+      uint32_t o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        o[i] = first ? p[i] : __float_as_uint(__fadd_rn(__uint_as_float(t[i]), __uint_as_float(p[i])));
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+          "%14, %15, %16};" ::"r"(tT + col),
+          "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]),
+          "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15])
+          : "memory");
+    }
+  }
+}
 
 __device__ __forceinline__ uint32_t f32x_zero_taps(const ConvGemmShape& s, int n0, int bn) {
   if (s.zero_taps == 0 || s.phase_cols % bn != 0) return 0;
@@ -245,38 +285,7 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int pb = chunk % PBUFS;
         ptx::mbar_wait_sleepy(&pfull[pb], (uint32_t)(chunk / PBUFS) & 1u);
         ptx::tc_fence_after();
-        // T[rows of this warp, its column half] (+)= P, 32 columns at a time (16 for the narrowest tiles)
-        constexpr int PIECE = (BN / 2) >= 32 ? 32 : 16;
-#pragma unroll 1
-        for (int c = 0; c < (BN / 2) / PIECE; ++c) {
-          const uint32_t col = half * (BN / 2) + c * PIECE;
-          if constexpr (PIECE == 32) {
-            uint32_t p[32], t[32];
-            ptx::tmem_ld_32x32(tm_P + pb * BN + lane_off + col, p);
-            if (!first) ptx::tmem_ld_32x32(tm_T + lane_off + col, t);
-            ptx::tmem_ld_wait();
-            if (!first) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) p[i] = __float_as_uint(__fadd_rn(__uint_as_float(t[i]), __uint_as_float(p[i])));
-            }
-            tmem_st_32x32(tm_T + lane_off + col, p);
-          } else {
-            uint32_t p[16], t[16];
-            ptx::tmem_ld_32x16(tm_P + pb * BN + lane_off + col, p);
-            if (!first) ptx::tmem_ld_32x16(tm_T + lane_off + col, t);
-            ptx::tmem_ld_wait();
-            uint32_t o[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              o[i] = first ? p[i] : __float_as_uint(__fadd_rn(__uint_as_float(t[i]), __uint_as_float(p[i])));
-            asm volatile(
-                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-                "%14, %15, %16};" ::"r"(tm_T + lane_off + col),
-                "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]),
-                "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15])
-                : "memory");
-          }
-        }
+        f32x_add_partial<BN>(tm_T + lane_off, tm_P + pb * BN + lane_off, half, first);
         tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
@@ -349,6 +358,242 @@ static int launch_f32x_cfg(const __nv_bfloat16* A2, const __nv_bfloat16* W2, con
   return DC_OK;
 }
 
+// ---------------------------------------------------------------- weights-stationary form for the narrow layers
+// C = BK and N = BN in {32, 64} (decoder stages 3 and 4, plain Conv1d): the generic kernel above re-loads the
+// activation box once per tap, 54 B of L2 -> SM traffic per output element at C = 32, k = 11 against 16 B of HBM traffic,
+// and runs at the L2 bandwidth (10 TB/s) instead of the HBM roof.  Here all J taps of [Whi | Wmid] stay in shared memory
+// for the whole launch, the activation tile [hi, mid] is loaded ONCE per row tile with its (J - 1) dil halo, and the taps
+// are row-shifted UMMA descriptors into it (as in conv_ws.cu).  Chunking, partial accumulators and the epilogue are the
+// generic kernel's (a chunk = the taps that make K = 256 per term), except that the eight consumer warps form two groups
+// with one total accumulator each and take alternate tiles.
+struct F32xWsLayout {
+  int w_bytes, a_half /* one of the two activation boxes, 1024-aligned */, stages, a_off, stg_off, bar_off, total, ra;
+};
+template <int BN, int BK>
+static F32xWsLayout f32x_ws_layout(int J, int dil) {
+  F32xWsLayout l;
+  l.ra = (128 + (J - 1) * dil + 7) / 8 * 8;
+  l.w_bytes = J * 2 * BN * BK * 2;
+  l.a_half = (l.ra * BK * 2 + 1023) / 1024 * 1024;
+  const int stg_bytes = 8 * 32 * f32x::Cfg<BN>::CW * 4;
+  const int budget = (BK == 32 ? 113 * 1024 : 232448) - 1024 - 256 - stg_bytes - l.w_bytes;  // BK = 32: two CTAs per SM
+  l.stages = budget / (2 * l.a_half);
+  if (l.stages > 3) l.stages = 3;
+  l.a_off = l.w_bytes;
+  l.stg_off = l.a_off + (l.stages > 0 ? l.stages : 0) * 2 * l.a_half;
+  l.bar_off = l.stg_off + stg_bytes;
+  l.total = l.bar_off + 256 + 1024;
+  return l;
+}
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(320, BK == 32 ? 2 : 1)
+gemm_f32x_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvGemmShape s,
+                    Epilogue ep, int variant, int tiles_per_clip, int total_tiles, F32xWsLayout lay) {
+  using namespace f32x;
+  // two consumer groups of 4 warps on alternate tiles, each with its own total accumulator T and its own ring of two
+  // partial accumulators (a group only ever waits for the NEXT phase of its own barriers): T[2] + P[2][2]
+  constexpr int SW = BK * 2, PBUFS = 2, TMEM_COLS = 6 * BN <= 256 ? 256 : 512, CW = Cfg<BN>::CW;
+  static_assert(6 * BN <= 512, "TMEM columns");
+  constexpr int B_BYTES = BN * BK * 2, TAPS_PER_CHUNK = 256 / BK;
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;                                                  // [J][hi, mid][BN][BK]
+  uint8_t* sA = smem + lay.a_off;                                      // [stages][hi, mid][ra][BK]
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem + lay.bar_off);   // [3]
+  uint64_t* aempty = afull + 3;                                        // [3]
+  uint64_t* pfull = aempty + 3;                                        // [2 groups][PBUFS]
+  uint64_t* pempty = pfull + 2 * PBUFS;                                // [2 groups][PBUFS]
+  uint64_t* wbar = pempty + 2 * PBUFS;                                 // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int stages = lay.stages, J = s.J;
+  const int chunks_per_tile = (J + TAPS_PER_CHUNK - 1) / TAPS_PER_CHUNK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < 3; ++i) {
+        ptx::mbar_init(&afull[i], 1);
+        ptx::mbar_init(&aempty[i], 1);
+      }
+      for (int i = 0; i < 2 * PBUFS; ++i) {
+        ptx::mbar_init(&pfull[i], 1);
+        ptx::mbar_init(&pempty[i], 4);
+      }
+      ptx::mbar_init(wbar, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_T = tmem_base, tm_P = tmem_base + 2 * BN;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer: the weights once, then one tile per stage
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(wbar, (uint32_t)lay.w_bytes);
+      for (int j = 0; j < J; ++j) {
+        ptx::tma_load_2d(sW + (2 * j) * B_BYTES, &tmW, wbar, j * 2 * BK, 0);            // W hi of tap j
+        ptx::tma_load_2d(sW + (2 * j + 1) * B_BYTES, &tmW, wbar, j * 2 * BK + BK, 0);   // W mid
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t a_bytes = (uint32_t)(2 * lay.ra * BK * 2);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int clip = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * 128;
+        ptx::mbar_wait(&aempty[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&afull[stage], a_bytes);
+        uint8_t* sp = sA + stage * 2 * lay.a_half;
+        ptx::tma_load_3d(sp, &tmA, &afull[stage], 0, t0 + s.shift0, clip);                // A hi, rows t0 + shift0 ..
+        ptx::tma_load_3d(sp + lay.a_half, &tmA, &afull[stage], BK, t0 + s.shift0, clip);  // A mid
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (ptx::elect_one()) {
+      ptx::mbar_wait(wbar, 0);
+      const uint32_t w_base = ptx::smem_u32(sW);
+      const uint32_t tap_step = (uint32_t)(s.dil * SW);   // bytes: tap j reads tile rows r + j * dil
+      int stage = 0, it = 0;
+      int gchunk[2] = {0, 0};   // chunks issued so far for each consumer group
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int g = it & 1;
+        ptx::mbar_wait(&afull[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t a_hi0 = ptx::smem_u32(sA + stage * 2 * lay.a_half), a_mid0 = a_hi0 + lay.a_half;
+        for (int j0 = 0; j0 < J; j0 += TAPS_PER_CHUNK) {
+          const int chunk = g ? gchunk[1]++ : gchunk[0]++;
+          const int pb = g * PBUFS + chunk % PBUFS;
+          ptx::mbar_wait(&pempty[pb], ((uint32_t)(chunk / PBUFS) & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tm_P + pb * BN;
+          const int j1 = j0 + TAPS_PER_CHUNK < J ? j0 + TAPS_PER_CHUNK : J;
+          for (int j = j0; j < j1; ++j) {
+            const uint32_t a_hi = a_hi0 + j * tap_step, a_mid = a_mid0 + j * tap_step;
+            const uint32_t w_hi = w_base + (2 * j) * B_BYTES, w_mid = w_hi + B_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t dah = ptx::make_smem_desc<SW>(a_hi + k * 32), dam = ptx::make_smem_desc<SW>(a_mid + k * 32);
+              const uint64_t dwh = ptx::make_smem_desc<SW>(w_hi + k * 32), dwm = ptx::make_smem_desc<SW>(w_mid + k * 32);
+              ptx::mma_bf16_ss(d_tmem, dam, dwh, IDESC, (j > j0 || k != 0) ? 1u : 0u);
+              ptx::mma_bf16_ss(d_tmem, dah, dwm, IDESC, 1u);
+              ptx::mma_bf16_ss(d_tmem, dah, dwh, IDESC, 1u);
+            }
+          }
+          if (j1 == J) ptx::mma_commit(&aempty[stage]);
+          ptx::mma_commit(&pfull[pb]);
+        }
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ chunk adders + epilogue: 2 groups x 4 warps
+    // A warp covers its TMEM lane quarter x all BN columns of the tiles of its group, so that two tiles are in their
+    // (DRAM-latency-bound) epilogue at any time.
+    float* stg = reinterpret_cast<float*>(smem + lay.stg_off) + (warp - 2) * (32 * CW);
+    const int group = (warp - 2) >> 2, q = warp & 3;
+    const int wid = 2 + ((warp - 2) & 3);      // epilogue_tile's warp id for column half 0: wid % 4 == warp % 4
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tm_Tg = tm_T + group * BN;
+    int chunk = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != group) continue;
+      const int clip = tile / tiles_per_clip, t0 = (tile % tiles_per_clip) * 128;
+      epilogue_prefetch(ep, clip, s.T, t0 + q * 32, 0, BN, lane);
+      for (int c = 0; c < chunks_per_tile; ++c, ++chunk) {
+        const int pb = group * PBUFS + chunk % PBUFS;   // `chunk` counts this group's chunks
+        ptx::mbar_wait_sleepy(&pfull[pb], (uint32_t)(chunk / PBUFS) & 1u);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) f32x_add_partial<BN>(tm_Tg + lane_off, tm_P + pb * BN + lane_off, hh, c == 0);
+        tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&pempty[pb]);
+      }
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) epilogue_tile<BN, CW>(ep, variant, stg, tm_Tg, clip, t0, 0, s.T, wid + 4 * hh, lane);
+      ptx::tc_fence_before();
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int BK>
+static bool f32x_ws_fits(const ConvGemmShape& s) {
+  if (!DC_F32X_WS || s.C != BK || s.N != BN || s.J < 2 || s.zero_taps != 0 || s.phase_cols != 0) return false;
+  const F32xWsLayout l = f32x_ws_layout<BN, BK>(s.J, s.dil);
+  return l.ra <= 256 && l.stages >= 2;
+}
+
+template <int BN, int BK>
+static int launch_f32x_ws(const __nv_bfloat16* A2, const __nv_bfloat16* W2, const ConvGemmShape& s, const Epilogue& e,
+                          cudaStream_t st, int sm_count) {
+  const F32xWsLayout lay = f32x_ws_layout<BN, BK>(s.J, s.dil);
+  static std::atomic<unsigned> attr_dev_mask{0u};
+  int dev = 0;
+  DC_CUDA(cudaGetDevice(&dev));
+  if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
+    DC_CUDA(cudaFuncSetAttribute(gemm_f32x_ws_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 BK == 32 ? 113 * 1024 : 232448));
+    attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
+  }
+  const int tiles_per_clip = (s.T + 127) / 128;
+  const long long total = (long long)s.B * tiles_per_clip;
+  DC_CHECK(total > 0 && total < (1ll << 31), DC_ERR_SHAPE, "gemm_f32x_ws: bad tile count");
+  CUtensorMap tmA, tmW;
+  {
+    const uint64_t dims[3] = {(uint64_t)2 * s.C, (uint64_t)s.T, (uint64_t)s.B};
+    const uint64_t strides[2] = {(uint64_t)2 * s.C * 2, (uint64_t)s.T * 2 * s.C * 2};
+    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)lay.ra, 1};
+    DC_TRY(make_tmap_bf16(&tmA, A2, 3, dims, strides, box, BK * 2));
+  }
+  {
+    const uint64_t K = (uint64_t)s.J * 2 * s.C;
+    const uint64_t dims[2] = {K, (uint64_t)s.N};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    DC_TRY(make_tmap_bf16(&tmW, W2, 2, dims, strides, box, BK * 2));
+  }
+  const long long slots = (long long)sm_count * (BK == 32 ? 2 : 1);
+  const int grid = (int)(total < slots ? total : slots);
+  {
+    const double rows = (double)s.B * s.T;
+    const double macs = rows * s.N * s.J * s.C * s.alg_scale;
+    const int esig = (e.act ? 1 : 0) | (e.gamma ? 2 : 0) | (e.res ? 4 : 0) | (e.add1 ? 8 : 0) |
+                     (e.out0 ? (e.out0_dt == DT_F32 ? 16 : 32) : 0) | (e.out1 ? 32 : 0);
+    const double out_bytes = (e.out0 ? 4.0 : 0.0) + (e.out1 ? 4.0 : 0.0) + (e.res ? 4.0 : 0.0) + (e.add1 ? 8.0 : 0.0);
+    ProfScope ps(PC_GEMM_F32, 2.0 * macs, rows * s.C * 4.0 + (double)s.N * s.J * s.C * 4.0 + rows * s.N * out_bytes, st,
+                 "xws<%d,%d>|C%d N%d J%d d%d e%d", BN, BK, s.C, s.N, s.J, s.dil, esig);
+    gemm_f32x_ws_kernel<BN, BK><<<grid, 320, lay.total, st>>>(tmA, tmW, s, e, epilogue_variant(e), tiles_per_clip, (int)total,
+                                                            lay);
+  }
+  ++g_launches_f32x;
+  DC_CUDA(cudaGetLastError());
+  return DC_OK;
+}
+
 bool gemm_f32x_supported(const ConvGemmShape& s) { return s.C % 32 == 0 && s.N % 32 == 0 && s.J >= 1; }
 
 // A2: (B, T, 2C) bf16 [hi | mid] of the fp32 activations (launch_split_f32); W2: [N][J][2C] bf16 [hi | mid] per tap.
@@ -360,6 +605,8 @@ int launch_gemm_f32x(const __nv_bfloat16* A2, const __nv_bfloat16* W2, const Con
     s.T = s.B * s.T;
     s.B = 1;
   }
+  if (f32x_ws_fits<32, 32>(s)) return launch_f32x_ws<32, 32>(A2, W2, s, e, st, sm_count);
+  if (f32x_ws_fits<64, 64>(s)) return launch_f32x_ws<64, 64>(A2, W2, s, e, st, sm_count);
   if (s.C % 64 == 0 && !(DC_F32X_NARROW_BK32 && s.N % 128 != 0)) {
     if (s.N % 128 == 0) return launch_f32x_cfg<128, 64>(A2, W2, s, e, st, sm_count);
     if (s.N % 64 == 0) return launch_f32x_cfg<64, 64>(A2, W2, s, e, st, sm_count);

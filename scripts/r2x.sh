@@ -1,1 +1,2 @@
-CLIPS=64 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_ws_pair_kernel" --launch-skip 12 --launch-count 2 -f -o gpurun_out/r2_ncu_ws2 python scripts/bench_stage.py generator conv_ws > gpurun_out/r2_ncu_ws2.log 2>&1; echo "ncu ws rc=$?"
+CLIPS=64 timeout 600 ncu --set full --clock-control none -k regex:conv_tsw_kernel --launch-skip 59 --launch-count 5 -f -o gpurun_out/r2_ncu_tsw3 python scripts/bench_stage.py generator conv_tsw > gpurun_out/r2_ncu_tsw3.log 2>&1; echo "ncu rc=$?"
+ls -la gpurun_out/r2_ncu_tsw3.ncu-rep
