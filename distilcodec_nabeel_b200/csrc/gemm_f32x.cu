@@ -72,6 +72,13 @@ int launch_split_f32(const float* in, __nv_bfloat16* out, size_t rows, int C, cu
 #ifndef DC_F32X_PREFETCH
 #define DC_F32X_PREFETCH 1
 #endif
+// CTA pairs with weight multicast for the 128-wide tiles.  Measured (64 clips, fp32 mode, `--opt cta_pairs=1|2`, two
+// alternating runs): 302.0 / 304.4 ms without, 307.2 / 303.4 ms with, identical codes — no gain, so off by default.  The
+// 128 x 128 x 16 MMAs of this kernel read 8 KB of shared-memory operands per 64 tensor cycles, the whole 128 B/clk port,
+// and the TMA fills of the stages take another 85 B/clk of it: the shared-memory port bounds the kernel, not L2.
+#ifndef DC_F32X_PAIRS
+#define DC_F32X_PAIRS 0
+#endif
 #ifndef DC_F32X_WS            // weights-stationary kernel for the C = N = 32 / 64 layers
 #define DC_F32X_WS 1
 #endif
@@ -159,14 +166,24 @@ __device__ __forceinline__ uint32_t f32x_zero_taps(const ConvGemmShape& s, int n
   return (s.zero_taps >> ((n0 / s.phase_cols) * s.J)) & ((1u << s.J) - 1u);
 }
 
-template <int BN, int BK>
-__global__ void __launch_bounds__(320, f32x::Smem<BN, BK>::CTAS_PER_SM)
+// CL = 2 (BN = 128): thread-block clusters of two CTAs on ADJACENT row tiles of the same N block: each CTA loads one half
+// (64 of the 128 rows) of Whi and Wmid and TMA-multicasts it into both CTAs' stages, as in gemm_tc / conv_tsw.  The wide
+// fp32 layers re-load a 64 KB stage per 12 MMAs = 85 B per clock and SM (10.9 TB/s of L2 reads on k = 11, C = 256); the pair
+// takes 16 of those 64 KB off L2.  See DC_F32X_PAIRS for what it bought.
+template <int BN, int BK, int CL>
+__global__ void __launch_bounds__(320, CL == 2 ? 1 : f32x::Smem<BN, BK>::CTAS_PER_SM)
 gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvGemmShape s,
                  Epilogue ep, int variant, int tiles_per_clip, int m_tiles, int n_tiles) {
   using namespace f32x;
   using L = Smem<BN, BK>;
   constexpr int SW = BK * 2, PBUFS = Cfg<BN>::PBUFS, TMEM_COLS = Cfg<BN>::TMEM_COLS, CW = Cfg<BN>::CW;
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(128, BN);
+  static_assert(CL == 1 || BN == 128, "weight multicast splits the 128 weight rows into two boxes of 64");
+  const int rank = CL == 2 ? (int)ptx::cluster_ctarank() : 0;
+  const int worker = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_items = CL == 2 ? (m_tiles + 1) / 2 : m_tiles;
+  auto item_m_blk = [&](int item) { return CL == 2 ? 2 * (item / n_tiles) + rank : item / n_tiles; };
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -187,7 +204,7 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       for (int i = 0; i < kStages; ++i) {
         ptx::mbar_init(&full[i], 1);
-        ptx::mbar_init(&empty[i], 1);
+        ptx::mbar_init(&empty[i], CL);   // released by the MMAs of every CTA the stage's weight boxes are multicast to
       }
       for (int i = 0; i < PBUFS; ++i) {
         ptx::mbar_init(&pfull[i], 1);
@@ -200,11 +217,12 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) ptx::cluster_sync();   // the peer's barriers exist before anything is multicast to them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_T = tmem_base, tm_P = tmem_base + BN;
 
-  const int total_tiles = m_tiles * n_tiles;
+  const int total_tiles = m_items * n_tiles;
   const int kchunks = s.C / BK;
 
   if (warp == 0) {
@@ -212,8 +230,8 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
+        const int m_blk = item_m_blk(tile), n_blk = tile % n_tiles;
         const int clip = m_blk / tiles_per_clip, t0 = (m_blk % tiles_per_clip) * 128, n0 = n_blk * BN;
         const uint32_t skip = f32x_zero_taps(s, n0, BN);
         for (int j = 0; j < s.J; ++j) {
@@ -225,8 +243,15 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* sp = smem + stage * L::STAGE_BYTES;
             ptx::tma_load_3d(sp, &tmA, &full[stage], kc * BK, trow, clip);                                  // A hi
             ptx::tma_load_3d(sp + L::A_BYTES, &tmA, &full[stage], s.C + kc * BK, trow, clip);               // A mid
-            ptx::tma_load_2d(sp + 2 * L::A_BYTES, &tmW, &full[stage], j * 2 * s.C + kc * BK, n0);           // W hi
-            ptx::tma_load_2d(sp + 2 * L::A_BYTES + L::B_BYTES, &tmW, &full[stage], j * 2 * s.C + s.C + kc * BK, n0);  // W mid
+            if constexpr (CL == 2) {   // this CTA's 64 rows of W hi and W mid, into both CTAs
+              ptx::tma_load_2d_multicast(sp + 2 * L::A_BYTES + rank * (L::B_BYTES / 2), &tmW, &full[stage],
+                                         j * 2 * s.C + kc * BK, n0 + rank * (BN / 2), (uint16_t)3);
+              ptx::tma_load_2d_multicast(sp + 2 * L::A_BYTES + L::B_BYTES + rank * (L::B_BYTES / 2), &tmW, &full[stage],
+                                         j * 2 * s.C + s.C + kc * BK, n0 + rank * (BN / 2), (uint16_t)3);
+            } else {
+              ptx::tma_load_2d(sp + 2 * L::A_BYTES, &tmW, &full[stage], j * 2 * s.C + kc * BK, n0);           // W hi
+              ptx::tma_load_2d(sp + 2 * L::A_BYTES + L::B_BYTES, &tmW, &full[stage], j * 2 * s.C + s.C + kc * BK, n0);  // W mid
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -238,7 +263,7 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int chunk = 0;   // running chunk counter over all tiles of this CTA (the adders count the same way)
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
         const int n0m = (tile % n_tiles) * BN;
         const int live = (s.J - __popc(f32x_zero_taps(s, n0m, BN))) * kchunks;  // stages of this tile
         for (int st0 = 0; st0 < live; st0 += kChunkStages, ++chunk) {
@@ -261,7 +286,8 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               ptx::mma_bf16_ss(d_tmem, dah, dwm, IDESC, 1u);
               ptx::mma_bf16_ss(d_tmem, dah, dwh, IDESC, 1u);
             }
-            ptx::mma_commit(&empty[stage]);
+            if constexpr (CL == 2) ptx::mma_commit_multicast(&empty[stage], (uint16_t)3);
+            else ptx::mma_commit(&empty[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
           ptx::mma_commit(&pfull[pb]);
@@ -275,11 +301,12 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int half = (warp - 2) >> 2;         // which half of the tile's columns (as epilogue_tile splits them)
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     int chunk = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+    for (int tile = worker; tile < total_tiles; tile += n_workers) {
+      const int m_blk = item_m_blk(tile), n_blk = tile % n_tiles;
       const int clip = m_blk / tiles_per_clip, t0 = (m_blk % tiles_per_clip) * 128, n0 = n_blk * BN;
       const int live = (s.J - __popc(f32x_zero_taps(s, n0, BN))) * kchunks;
-      epilogue_prefetch(ep, clip, s.T, t0 + q * 32, n0 + half * (BN / 2), BN / 2, lane);
+      const bool ghost = m_blk >= m_tiles;   // CL = 2, odd number of row tiles: computed on zero rows, never stored
+      if (!ghost) epilogue_prefetch(ep, clip, s.T, t0 + q * 32, n0 + half * (BN / 2), BN / 2, lane);
       bool first = true;
       for (int st0 = 0; st0 < live; st0 += kChunkStages, ++chunk) {
         const int pb = chunk % PBUFS;
@@ -294,13 +321,14 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       // the tile's total is complete in T (this warp's region was written by this warp only): the usual epilogue
       ptx::tc_fence_after();
-      epilogue_tile<BN, CW>(ep, variant, stg, tm_T, clip, t0, n0, s.T, 2 + ((warp - 2) & 7), lane);
+      if (!ghost) epilogue_tile<BN, CW>(ep, variant, stg, tm_T, clip, t0, n0, s.T, 2 + ((warp - 2) & 7), lane);
       ptx::tc_fence_before();
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) ptx::cluster_sync();   // no CTA exits while its peer may still multicast into it
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -308,7 +336,7 @@ gemm_f32x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------- launcher
-template <int BN, int BK>
+template <int BN, int BK, int CL = 1>
 static int launch_f32x_cfg(const __nv_bfloat16* A2, const __nv_bfloat16* W2, const ConvGemmShape& s, const Epilogue& e,
                            cudaStream_t st, int sm_count) {
   using L = f32x::Smem<BN, BK>;
@@ -316,7 +344,7 @@ static int launch_f32x_cfg(const __nv_bfloat16* A2, const __nv_bfloat16* W2, con
   int dev = 0;
   DC_CUDA(cudaGetDevice(&dev));
   if (!(attr_dev_mask.load(std::memory_order_acquire) & (1u << dev))) {
-    DC_CUDA(cudaFuncSetAttribute(gemm_f32x_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    DC_CUDA(cudaFuncSetAttribute(gemm_f32x_kernel<BN, BK, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_dev_mask.fetch_or(1u << dev, std::memory_order_release);
   }
   const int tiles_per_clip = (s.T + 127) / 128;
@@ -334,12 +362,12 @@ static int launch_f32x_cfg(const __nv_bfloat16* A2, const __nv_bfloat16* W2, con
     const uint64_t K = (uint64_t)s.J * 2 * s.C;
     const uint64_t dims[2] = {K, (uint64_t)s.N};
     const uint64_t strides[1] = {K * 2};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(BN / CL)};   // CL = 2: each CTA of a pair loads half the rows
     DC_TRY(make_tmap_bf16(&tmW, W2, 2, dims, strides, box, BK * 2));
   }
-  const long long total = m_tiles * n_tiles;
-  const long long slots = (long long)sm_count * L::CTAS_PER_SM;
-  const int grid = (int)(total < slots ? total : slots);
+  const long long total = ((m_tiles + CL - 1) / CL) * n_tiles;
+  const long long slots = CL == 2 ? sm_count / 2 : (long long)sm_count * L::CTAS_PER_SM;
+  const int grid = (int)(total < slots ? total : slots) * CL;
   {
     const double rows = (double)s.B * s.T;
     const double macs = rows * s.N * s.J * s.C * s.alg_scale;
@@ -347,11 +375,25 @@ static int launch_f32x_cfg(const __nv_bfloat16* A2, const __nv_bfloat16* W2, con
                      (e.out0 ? (e.out0_dt == DT_F32 ? 16 : 32) : 0) | (e.out1 ? 32 : 0);
     const double out_bytes = (e.out0 ? 4.0 : 0.0) + (e.out1 ? 4.0 : 0.0) + (e.res ? 4.0 : 0.0) + (e.add1 ? 8.0 : 0.0);
     ProfScope ps(PC_GEMM_F32, 2.0 * macs, rows * s.C * 4.0 + (double)s.N * s.J * s.C * 4.0 + rows * s.N * out_bytes, st,
-                 "x<%d,%d>|C%d N%d J%d d%d e%d", BN, BK, s.C, s.N, s.J, s.dil, esig);
+                 CL == 2 ? "x<%d,%d>x2|C%d N%d J%d d%d e%d" : "x<%d,%d>|C%d N%d J%d d%d e%d", BN, BK, s.C, s.N, s.J, s.dil,
+                 esig);
     Epilogue eg = e;
     eg.prefetch = DC_F32X_PREFETCH ? e.prefetch : 0;
-    gemm_f32x_kernel<BN, BK><<<grid, 320, L::TOTAL, st>>>(tmA, tmW, s, eg, epilogue_variant(e), tiles_per_clip, (int)m_tiles,
-                                                         n_tiles);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    DC_CUDA(cudaLaunchKernelEx(&cfg, gemm_f32x_kernel<BN, BK, CL>, tmA, tmW, s, eg, epilogue_variant(e), tiles_per_clip,
+                               (int)m_tiles, n_tiles));
   }
   ++g_launches_f32x;
   DC_CUDA(cudaGetLastError());
@@ -608,7 +650,10 @@ int launch_gemm_f32x(const __nv_bfloat16* A2, const __nv_bfloat16* W2, const Con
   if (f32x_ws_fits<32, 32>(s)) return launch_f32x_ws<32, 32>(A2, W2, s, e, st, sm_count);
   if (f32x_ws_fits<64, 64>(s)) return launch_f32x_ws<64, 64>(A2, W2, s, e, st, sm_count);
   if (s.C % 64 == 0 && !(DC_F32X_NARROW_BK32 && s.N % 128 != 0)) {
-    if (s.N % 128 == 0) return launch_f32x_cfg<128, 64>(A2, W2, s, e, st, sm_count);
+    if (s.N % 128 == 0) {
+      const bool pair = DC_F32X_PAIRS && s.cluster == 2 && (long long)s.B * ((s.T + 127) / 128) >= 2 && sm_count >= 2;
+      return pair ? launch_f32x_cfg<128, 64, 2>(A2, W2, s, e, st, sm_count) : launch_f32x_cfg<128, 64>(A2, W2, s, e, st, sm_count);
+    }
     if (s.N % 64 == 0) return launch_f32x_cfg<64, 64>(A2, W2, s, e, st, sm_count);
     return launch_f32x_cfg<32, 64>(A2, W2, s, e, st, sm_count);
   }
