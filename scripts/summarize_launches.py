@@ -18,7 +18,7 @@ def short(n):
 
 starts = [i for i, r in enumerate(rows) if "transpose_ncl_to_nlc" in r[0]]      # first kernel of every step
 step_len = starts[1] - starts[0]
-s0 = starts[3]                                                                   # after 3 warm-up steps = the timed step
+s0 = starts[3]                                                                   # a step after the warm-up passes
 step = rows[s0:s0 + step_len]
 tot = sum(r[3] for r in step)
 agg = collections.OrderedDict()
@@ -26,7 +26,7 @@ for n, g, b, t in step:
     a = agg.setdefault(short(n), [0, 0.0])
     a[0] += 1
     a[1] += t
-out = [f"# ncu launch list summary, {tag}: python bench.py --steps 1 --warmup 3 --no-cpu-baseline (B200, "
+out = [f"# ncu launch list summary, {tag}: python bench.py --steps 2 --warmup 1 --no-cpu-baseline under ncu -c 1500 (B200, "
        "ncu --metrics gpu__time_duration.sum --clock-control none)",
        f"# the timed step = launches {s0}..{s0 + step_len - 1} of the list ({step_len} launches, {tot / 1e6:.1f} ms serialised); "
        "durations are cold-cache and serialised: compare SHARES with bench.py's `kernels`, not absolutes",
