@@ -542,7 +542,9 @@ int launch_conv_tsw(const __nv_bfloat16* A, const __nv_bfloat16* W, const ConvGe
 #ifdef DC_TSW_RES_CW32   // A/B builds: whole-line epilogue chunks + 3-stage ring for every residual layer
     if (pair) return launch_tsw<2, 32, 3, 2>(A, W, s, e, st, sm_count);
 #endif
-    if (s.J * s.C <= 1792 && s.N == 256)
+    // short K (k = 3 at C = 512, k <= 7 at C = 256): epilogue-bound, whole-line chunks beat the 4th weight stage
+    // (C = 512, k = 3: 3.59 -> 3.21 ms per launch)
+    if (s.J * s.C <= 1792)
       return pair ? launch_tsw<2, 32, 3, 2>(A, W, s, e, st, sm_count) : launch_tsw<2, 32, 3, 1>(A, W, s, e, st, sm_count);
     return pair ? launch_tsw<2, 16, 4, 2>(A, W, s, e, st, sm_count) : launch_tsw<2, 16, 4, 1>(A, W, s, e, st, sm_count);
   }
