@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdistilcodec_b200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "conv_ws.cu", "conv_pair.cu", "conv_ts.cu", "gemm_f32.cu", "gemm_f32x.cu", "pointwise.cu", "vq.cu", "mel.cu", "audio_io.cpp"]
+SOURCES = ["api.cu", "gemm_tc.cu", "conv_ws.cu", "conv_pair.cu", "conv_ts.cu", "conv_post.cu", "gemm_f32.cu", "gemm_f32x.cu", "pointwise.cu", "vq.cu", "mel.cu", "audio_io.cpp"]
 HEADERS = ["common.cuh", "ptx.cuh", "epilogue.cuh", os.path.join("..", "..", "include", "distilcodec_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -191,6 +191,8 @@ struct dc_handle_s {
   float* post_w = nullptr;  // [k][C_last] (device copy)
   float post_w_host[13 * 32] = {};  // passed to the kernel as a parameter (constant bank)
   float post_b = 0.f;
+  __nv_bfloat16* post_wt = nullptr;  // conv_post's block-Toeplitz weights [16][768] (conv_post.cu), bf16 mode
+  int post_tc = 1;                   // option "post_tc": conv_post on the tensor cores (bf16 mode)
   int post_C = 0;
 };
 
@@ -222,6 +224,7 @@ static void reset_packed(dc_handle_s* h) {
       for (auto& c : b)
         for (auto& d : c) d = Dense();
   h->post_w = nullptr;
+  h->post_wt = nullptr;
   h->post_C = 0;
   h->split_scratch = nullptr;
   h->split_cap = 0;
@@ -794,7 +797,13 @@ static int stage_generator(const dc_handle_s* h, const float* z, int B, int T, f
   }
   ar.release(m0);
   if (!dry)  // silu (folded above) -> conv_post -> tanh (generators.py:141-145)
-    DC_TRY(launch_conv_post_tanh(carry[cur], ad, h->post_w_host, h->post_b, wav, B, L, st));
+  {
+    if (ad == DT_BF16 && h->post_tc && h->post_wt && conv_post_tc_supported(L))
+      DC_TRY(launch_conv_post_tanh_tc(reinterpret_cast<const __nv_bfloat16*>(carry[cur]), h->post_wt, h->post_b, wav, B, L,
+                                      st, h->sm_count));
+    else
+      DC_TRY(launch_conv_post_tanh(carry[cur], ad, h->post_w_host, h->post_b, wav, B, L, st));
+  }
   return DC_OK;
 }
 
@@ -917,6 +926,8 @@ int dc_set_option(dc_handle h, const char* key, double value) {
   } else if (!strcmp(key, "pairx")) {
     DC_CHECK(value == 0.0 || value == 1.0 || value == 2.0, DC_ERR_ARG, "pairx must be 0, 1 or 2");
     h->pairx = (int)value;
+  } else if (!strcmp(key, "post_tc")) {
+    h->post_tc = value != 0.0;
   } else if (!strcmp(key, "epi_prefetch")) {
     h->epi_prefetch = (int)value;
   } else {
@@ -1127,6 +1138,12 @@ int dc_finalize(dc_handle h, void* stream) {
     cudaStreamSynchronize(st);
     cudaFree(scratch);
     if (rc) return rc;
+    {  // conv_post's block-Toeplitz operand for the tensor-core form (conv_post.cu); post_w_host is valid after the sync
+      std::vector<__nv_bfloat16> wt(16 * 768);
+      conv_post_toeplitz_weights(h->post_w_host, wt.data());
+      DC_TRY(dev_alloc(h, &h->post_wt, wt.size()));
+      DC_CUDA(cudaMemcpy(h->post_wt, wt.data(), wt.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    }
   }
   DC_CUDA(cudaStreamSynchronize(st));
   // the big raw matrices are no longer needed (1-D parameters stay: kernels read them in place)
@@ -1444,7 +1461,7 @@ int dc_profile_collect(dc_profile_row* rows, int cap, int* n) {
 uint64_t dc_launch_count(void) {
   return g_launches_api + gemm_tc_launch_count() + gemm_f32_launch_count() + pointwise_launch_count() +
          vq_launch_count() + conv_ws_launch_count() + mel_launch_count() + conv_ts_launch_count() +
-         conv_pairx_launch_count() + gemm_f32x_launch_count();
+         conv_pairx_launch_count() + gemm_f32x_launch_count() + conv_post_launch_count();
 }
 
 }  // extern "C"

@@ -186,6 +186,12 @@ int launch_gather_rows(const float* table, const int64_t* idx, int64_t nrows, in
                        float* out_f32 /*nullable*/, __nv_bfloat16* out_bf16 /*nullable*/, cudaStream_t st);
 int launch_conv_post_tanh(const void* in, int in_dt, const float* w_host /*[13][32], HOST memory*/, float bias,
                           float* out, int B, int L, cudaStream_t st);
+// conv_post.cu: the same layer on the tensor cores (bf16 input; block-Toeplitz over 8 samples)
+void conv_post_toeplitz_weights(const float* w /*[13][32], host*/, __nv_bfloat16* wt /*[16][768], host*/);
+bool conv_post_tc_supported(int L);
+int launch_conv_post_tanh_tc(const __nv_bfloat16* in, const __nv_bfloat16* wt /*device*/, float bias, float* out, int B,
+                             int L, cudaStream_t st, int sm_count);
+uint64_t conv_post_launch_count();
 // weight prepack helpers
 int launch_weight_norm_fold(const float* g, const float* v, float* w, int dim0, int inner, cudaStream_t st);
 struct PackDesc {

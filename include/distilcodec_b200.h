@@ -82,6 +82,7 @@ int dc_destroy(dc_handle h);
  * "pairx" (which fused kernel the C = 32 stage uses: 0 conv_ws_pair, 1 conv_pair on the fp32 stream, 2 [default]
  * conv_pair with the bf16 side buffer), "cta_pairs" (2 [default] = the tensor-bound kernels run as thread-block clusters of
  * two CTAs that TMA-multicast the weight / codebook tiles they share; 1 = single CTAs; results are bit-identical),
+ * "post_tc" (bf16 mode: 1 [default] = conv_post + tanh as a block-Toeplitz tensor-core GEMM, 0 = the CUDA-core kernel),
  * "epi_prefetch" (L2 prefetch of the residual / mean operands of the next tile: 1 [default] = where the layer is
  * HBM-latency-bound, 2 = also k = 7 at C = 256, 3 = every layer, 0 = never),
  * "fp32_tc" (DC_MODE_FP32 only: 1 [default] = dense layers on the tensor cores with split-bf16 operands and chunked fp32

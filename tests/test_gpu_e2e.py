@@ -315,6 +315,28 @@ def test_fp32_stream_pair_kernel_matches_oracle_and_the_two_kernel_form(variant)
 
 
 @pytest.mark.parametrize("variant", ["W0", "W1"])
+def test_conv_post_on_the_tensor_cores_matches_the_cuda_core_form(variant):
+    """conv_post + tanh as a block-Toeplitz GEMM over 8 samples (conv_post.cu, weights split hi + lo) against the
+    CUDA-core kernel with fp32 weights (pointwise.cu): same bf16 input, fp32 accumulation in both."""
+    eng = engine(variant, "bf16")
+    for B, T, seed in ((3, 37, 41), (2, 301, 42), (1, 1, 43)):
+        zd = (make_latents(B, T, seed=seed) * 0.5).transpose(1, 2).contiguous().to(eng.device)
+        try:
+            eng.set_option("post_tc", 0)
+            n0 = eng.launch_count()
+            y0 = eng.generator(zd)
+            n1 = eng.launch_count()
+            eng.set_option("post_tc", 1)
+            y1 = eng.generator(zd)
+            n2 = eng.launch_count()
+        finally:
+            eng.set_option("post_tc", 1)
+        assert n1 - n0 == n2 - n1                       # one launch either way
+        assert y0.shape == y1.shape == (B, 256 * T)
+        assert rel_err(y1, y0) < 2e-5, (B, T)
+
+
+@pytest.mark.parametrize("variant", ["W0", "W1"])
 def test_fp32_mode_on_tensor_cores_keeps_the_fp32_gate(variant):
     """DC_MODE_FP32 (the reference API's default, enable_bfloat16=False) with its dense layers on the tensor cores
     (option "fp32_tc": two-term bf16 split of both operands, three cross products, accumulation chunked to K <= 256 per
