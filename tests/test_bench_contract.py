@@ -56,5 +56,7 @@ def test_own_arm_prints_one_parseable_line():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r)
     assert r["bound"] in ("hbm", "tensor") and 0 < r["frac"] < 1.1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
     c = line["clocks"]
-    assert c["sm_mhz"] > 0 and c["sm_max_mhz"] >= c["sm_mhz"] and isinstance(c["reasons"], list)
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(c) and isinstance(c["reasons"], list)
+    if c["sm_mhz"] is not None:                         # a 2-step run of 8 clips may end before the first nvidia-smi sample
+        assert 0 < c["sm_mhz"] <= c["sm_max_mhz"]
     assert len(line["per_rank_ms"]) == 1
