@@ -59,6 +59,7 @@ SIGNATURES = {
     "dc_generator_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "dc_mel_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "dc_copy2d_async": (_i, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
+    "dc_conv_post_toeplitz_weights": (_i, [_vp, _vp]),
     "dc_audio_probe": (_i, [C.c_char_p, C.POINTER(DcAudioInfo)]),
     "dc_audio_resampled_length": (_i, [_i64, _i, _i, C.POINTER(_i64)]),
     "dc_audio_resample": (_i, [_vp, _i64, _i, _i, _i, C.c_double, _vp, _i64, C.POINTER(_i64), _i]),

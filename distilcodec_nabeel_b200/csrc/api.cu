@@ -1284,6 +1284,13 @@ int dc_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pit
   return DC_OK;
 }
 
+int dc_conv_post_toeplitz_weights(const float* w, uint16_t* wt) {
+  DC_CHECK(w && wt, DC_ERR_ARG, "bad argument to dc_conv_post_toeplitz_weights");
+  static_assert(sizeof(__nv_bfloat16) == sizeof(uint16_t), "bf16 bit patterns");
+  conv_post_toeplitz_weights(w, reinterpret_cast<__nv_bfloat16*>(wt));
+  return DC_OK;
+}
+
 int dc_ncl_to_nlc(const float* in_dev, float* out_dev, int B, int C, int T, void* stream) {
   DC_CHECK(in_dev && out_dev && B > 0 && C > 0 && T > 0, DC_ERR_ARG, "bad argument to dc_ncl_to_nlc");
   return launch_transpose_ncl_to_nlc(in_dev, out_dev, DT_F32, B, C, T, reinterpret_cast<cudaStream_t>(stream));

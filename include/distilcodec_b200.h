@@ -164,6 +164,14 @@ int dc_mel_forward(dc_handle h, const float* audio_dev, int B, int Ls, float* me
 int dc_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
                     void* stream);
 
+/* Host utility (no CUDA call): the block-Toeplitz operand the tensor-core form of conv_post + tanh
+ * (models/generators.py:141-145) multiplies by.  w: the weight-norm-folded conv_post weight as [13 taps][32 channels]
+ * fp32; wt: [16][768] bf16 bit patterns, rows 0-7 = bf16(W), rows 8-15 = bf16(W - bf16(W)), with
+ * W[r][o*256 + i*32 + c] = w[8*(o-1) + i - r + 6][c] (0 outside the 13 taps), so that
+ * y[8q + r] = sum_o sum_k S[q - 1 + o][k] * W[r][o*256 + k] for the (L/8, 256) view S of the (L, 32) input.
+ * dc_finalize() calls it; exported so that the layout can be checked against the plain convolution without a GPU. */
+int dc_conv_post_toeplitz_weights(const float* w, uint16_t* wt);
+
 /* ---- audio file I/O + resample on the host -------------------------------------------
  * Replaces the reference's single-threaded librosa path that feeds the hot path:
  *   load_and_resample_audio  distil_codec.py:657-684  (librosa.load(sr=None, mono=False) + librosa.resample + mean)

@@ -82,3 +82,35 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "/root/reference" not in src, f
+
+
+def test_conv_post_toeplitz_operand_reproduces_the_convolution():
+    """conv_post + tanh runs as a GEMM over 8 consecutive samples on the tensor cores (csrc/conv_post.cu).  The operand
+    layout is host code: check it against Conv1d(32 -> 1, k13, pad 6) (models/generators.py:141-145) in numpy, with the
+    kernel's own indexing  y[8q + r] = sum_o S[q - 1 + o] . Wt[r][o*256 : (o+1)*256]  and zero padding at both ends."""
+    import ctypes
+
+    import numpy as np
+    import torch
+
+    lib = _abi.load()
+    rng = np.random.default_rng(5)
+    w = rng.standard_normal((13, 32)).astype(np.float32)          # [tap][channel]
+    wt = np.zeros((16, 768), dtype=np.uint16)
+    assert lib.dc_conv_post_toeplitz_weights(w.ctypes.data_as(ctypes.c_void_p), wt.ctypes.data_as(ctypes.c_void_p)) == 0
+    W = torch.from_numpy(wt.view(np.int16)).view(torch.bfloat16).float().numpy()          # bf16 bit patterns -> fp32
+    hi, lo = W[:8], W[8:]
+    np.testing.assert_array_equal(hi, torch.from_numpy(hi + lo).bfloat16().float().numpy())  # rows 0-7 = bf16(w)
+    Wsum = hi + lo                                                                           # = w to 16 mantissa bits
+    L = 8 * 37
+    s = rng.standard_normal((L, 32)).astype(np.float32)
+    ref = torch.nn.functional.conv1d(torch.from_numpy(s.T[None]), torch.from_numpy(w.T[None].copy()), padding=6)[0, 0].numpy()
+    S = np.zeros((L // 8 + 2, 256), dtype=np.float32)            # one zero super-row before and after = the padding
+    S[1:-1] = s.reshape(L // 8, 256)
+    y = np.zeros(L, dtype=np.float64)
+    for q in range(L // 8):
+        for o in range(3):
+            y[8 * q:8 * q + 8] += Wsum[:, o * 256:(o + 1) * 256].astype(np.float64) @ S[q + o].astype(np.float64)
+    assert np.abs(y - ref).max() < 2e-4 * np.abs(ref).max()      # weights rounded to 16 mantissa bits, nothing else
+    # every weight appears exactly 8 times (once per output phase r), the rest of the 16 x 768 operand is zero
+    assert np.count_nonzero(hi) == 8 * 13 * 32
